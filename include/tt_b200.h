@@ -1,0 +1,243 @@
+/*
+ * tt_b200.h — C ABI of libtt_b200.so: the B200-native (sm_100a) operator library for the
+ * ThinkTwice per-frame forward path.  It replaces `open_loop_training/ops` of the reference
+ * (OpenDriveLab/ThinkTwice) and the third-party native ops the path crosses (mmcv._ext
+ * ms_deform_attn / deform_conv / hard_voxelize, spconv, cuDNN/cuBLAS through torch.nn).
+ *
+ * Conventions (SURVEY.md §8b "External native ABIs"):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
+ *   - activations are fp32 channels-last: a feature map is [N][H][W][ld] floats, the logical
+ *     channels of a tensor live at [coff, coff + C) inside the pixel's `ld` floats, so a concat
+ *     is just several producers writing into one buffer;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), takes no locks, keeps no global
+ *     state except the last-error string, and NEVER calls exit(): 0 = ok, negative = tt_status;
+ *   - the caller owns and allocates all buffers.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to
+ * /root/reference/open_loop_training).
+ */
+#ifndef TT_B200_H_
+#define TT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tt_stream_t; /* cudaStream_t */
+
+typedef enum { TT_OK = 0, TT_ERR_INVALID = -1, TT_ERR_CUDA = -2, TT_ERR_UNSUPPORTED = -3 } tt_status;
+enum { TT_ACT_NONE = 0, TT_ACT_RELU = 1, TT_ACT_GELU = 2, TT_ACT_SIGMOID = 3, TT_ACT_SOFTPLUS = 4,
+       TT_ACT_SOFTPLUS_CLAMP = 5 /* clamp(softplus(x), min=1e-3): thinktwice_decoder.py:484 */ };
+enum { TT_RES_NONE = 0, TT_RES_SAME = 1, TT_RES_UP2_NEAREST = 2 };
+
+int tt_version(void);
+const char* tt_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long tt_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) voxel pooling — drop-in for the reference's only in-tree native op.
+ * Replaces: ops/voxel_pooling/src/voxel_pooling_forward.cpp:21-22 and
+ *           src/voxel_pooling_forward_cuda.cu:38-42 `voxel_pooling_forward_kernel_launcher`.
+ * Same argument list and ownership rules (caller zero-fills output_features [B][Y][X][C] and
+ * fills pos_memo [B][P][3] with -1; the op accumulates in place) but returns a status instead
+ * of exiting.  geom_xyz int32 [B][P][3] (x, y, z); input_features fp32 [B][P][C].
+ * Like the reference it accumulates with fp32 atomics (sum order unspecified), but with coalesced
+ * 128-bit feature loads and one 128-bit vector reduction per 4 channels.  The model itself uses
+ * tt_lift_splat below, which has no floating-point atomics.
+ * `workspace` must hold tt_voxel_pooling_workspace_bytes(...) bytes (may be NULL when that is 0).
+ */
+size_t tt_voxel_pooling_workspace_bytes(int batch_size, int num_points, int num_voxel_x, int num_voxel_y);
+int tt_voxel_pooling_forward(int batch_size, int num_points, int num_channels, int num_voxel_x, int num_voxel_y,
+                             int num_voxel_z, const int* geom_xyz, const float* input_features,
+                             float* output_features, int* pos_memo, void* workspace, tt_stream_t stream);
+
+/* Fused lift-splat: lss.py:582-632 (depth softmax, outer product with the context features,
+ * frustum geometry, voxel index, scatter-add) without the (B,N,D,H,W,C) intermediate.
+ *   depth_logits : [BN][fH][fW][ld_d] channels-last, D logits at [d_coff, d_coff + D)
+ *   context      : [BN][fH][fW][ld_c] channels-last, C features at [c_coff, c_coff + C)
+ *   mats         : [BN][2][16] fp32 row-major 4x4: ida^-1 and sensor2ego*intrin^-1 (lss.py:496,502)
+ *   frustum_u [fW], frustum_v [fH], frustum_d [D]: the image-plane / depth coordinates of the
+ *                  reference's `frustum` buffer (lss.py:454-471), passed in so both sides use the same floats
+ *   bev          : [B][Y][X][bev_ld] (+bev_coff), OVERWRITTEN (not accumulated); if `anti_transpose`
+ *                  the rot90(flip) of encoder_decoder_framework.py:241 is folded into the store.
+ * voxel index = trunc((p - lower) / size) exactly as lss.py:630-631 (`.int()` truncates toward 0).
+ */
+typedef struct {
+  int B, N, D, fH, fW, C;
+  int ld_d, d_coff, ld_c, c_coff;
+  float lower[3], size[3];       /* lower = (voxel_coord - voxel_size/2) as computed in fp32 by lss.py:630 */
+  int X, Y, Z;
+  int bev_ld, bev_coff;
+  int anti_transpose;
+} tt_lift_splat_desc;
+size_t tt_lift_splat_workspace_bytes(const tt_lift_splat_desc* d);
+int tt_lift_splat(const tt_lift_splat_desc* d, const float* depth_logits, const float* context, const float* mats,
+                  const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev, void* workspace,
+                  tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) implicit-GEMM convolution / linear layer.
+ * Replaces every torch.nn.Conv2d / ConvTranspose2d(k2s2) / Linear on the path (cuDNN/cuBLAS via
+ * torch) and, with `gather`, spconv SubMConv3d / SparseConv3d (N5).
+ *   y[pix(m)][y_coff + n] = act( sum_k A[m][k] * w[k][n] + bias[n] + res[...] + res2[...] )
+ *   A[m][k], k = tap * Cin_g + c : the input pixel of output row m under tap (kh, kw), channel
+ *   g*Cin_g + c, zero outside the image; or, when gather != NULL, row gather[m*taps + tap] of x
+ *   (-1 = zero row) — the sparse-conv rulebook.
+ *   w: packed [taps * Cin_g][Cout] fp32 (BatchNorm already folded in), bias [Cout] or NULL.
+ * Output row m = (n, oh, ow) is stored at pixel (n, oh*oy_mul + oy_add, ow*ox_mul + ox_add) of a
+ * [N][yH][yW][y_ld] buffer (a k2s2 transposed conv is four such calls).
+ * If m_count != NULL only the first *m_count rows (a device int) are computed.
+ * `impl`: 0 = auto, 1 = SIMT fp32 (exact), 2 = tcgen05 TF32x1, 3 = tcgen05 3xTF32 (fp32-class).
+ */
+typedef struct {
+  int N, H, W, Cin, x_ld, x_coff;
+  long long x_nstride, y_nstride;  /* floats between consecutive images; 0 = dense (H*W*x_ld, yH*yW*y_ld) */
+  int Cout, KH, KW, stride, pad, dil, groups;
+  int OH, OW;
+  int y_ld, y_coff, yH, yW, oy_mul, oy_add, ox_mul, ox_add;
+  int act;
+  int res_mode, res_ld, res_coff; /* res: same pixel grid as the output rows (SAME) or coarser (UP2_NEAREST) */
+  int res_H, res_W;               /* UP2_NEAREST: residual map size; source pixel = floor(o * res / O) */
+  int res2_ld, res2_coff;         /* optional second SAME residual */
+  int taps;                       /* gather mode: taps per row (KH=KW=1 then); else ignored */
+  int M;                          /* gather mode: row capacity; else ignored (N*OH*OW) */
+  int impl;
+} tt_conv_desc;
+int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
+              const float* res2, const int* gather, const int* m_count, float* y, tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) memory-bound helpers (torch elementwise / pooling / interpolation ops)
+ */
+/* NCHW fp32 -> channels-last with `ld` floats per pixel (channels >= C are zero-filled up to cpad) */
+int tt_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, int y_ld, int y_coff, int cpad,
+                    tt_stream_t stream);
+int tt_nhwc_to_nchw(const float* x, int x_ld, int x_coff, float* y, int N, int C, int H, int W, tt_stream_t stream);
+/* F.max_pool2d(x, 3, stride 2, padding 1) — mmdet ResNet stem */
+int tt_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, tt_stream_t stream);
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) — lss.py:267 */
+int tt_upsample2x_bilinear_ac(const float* x, float* y, int N, int H, int W, int C, tt_stream_t stream);
+/* mean over H*W -> [N][C] — lss.py:80 AdaptiveAvgPool2d */
+int tt_global_avgpool(const float* x, int x_ld, int x_coff, float* y, int N, int HW, int C, tt_stream_t stream);
+/* y[n][p][y_coff + c] = v[n][c] (bilinear resize of a 1x1 map == broadcast, lss.py:100-103) */
+int tt_broadcast_rows(const float* v, float* y, int N, int HW, int C, int y_ld, int y_coff, tt_stream_t stream);
+/* y = x * sigmoid(g[n][c]) — SELayer, lss.py:158 (g holds conv_expand output, pre-sigmoid) */
+int tt_se_gate(const float* x, const float* g, float* y, int N, int HW, int C, tt_stream_t stream);
+/* s[n][c] = 0.5*mean_hw + 0.5*max_hw — code/utils.py:90-91 */
+int tt_se_pool(const float* x, float* s, int N, int HW, int C, tt_stream_t stream);
+/* y = relu(x * sigmoid(g[n][c]) + shortcut) — code/utils.py:96,118-120 */
+int tt_se_apply(const float* x, const float* g, const float* shortcut, int sc_ld, int sc_coff, float* y, int y_ld,
+                int y_coff, int N, int HW, int C, tt_stream_t stream);
+/* out[i][j] = x[H-1-j][W-1-i] per image/channel: rot90(flip(x,[2]),1,[2,3]) — framework:241,246 */
+int tt_anti_transpose(const float* x, float* y, int N, int S, int C, tt_stream_t stream);
+/* dst[r][c] = src[src_row(r)][c], src_row = (r / rdiv) % rmod; strides in floats */
+int tt_copy2d(const float* src, int src_ld, float* dst, int dst_ld, int rows, int cols, int rdiv, int rmod,
+              tt_stream_t stream);
+/* LayerNorm over the last dim (eps 1e-5), rows x D, output stride y_ld */
+int tt_layernorm(const float* x, int x_ld, const float* gamma, const float* beta, float* y, int y_ld, int rows,
+                 int D, const int* row_count, tt_stream_t stream);
+/* elementwise: op 0: y = a + b; 1: y = (1 - a) * b; 2: y = (1 - a) * b + a * c; 3: y = act(a) */
+int tt_eltwise(int op, int act, const float* a, int a_ld, const float* b, int b_ld, const float* c, int c_ld, float* y,
+               int y_ld, int rows, int cols, tt_stream_t stream);
+int tt_fill(float* y, float v, long long n, tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) deformable convolution v1 — mmcv DeformConv2dPack (lss.py:189-197), 3x3, pad 1, stride 1,
+ * deform_groups 1.  Produces the sampled columns [N*H*W][groups][9][C/groups]; the grouped GEMM is
+ * tt_conv2d(KH=KW=1, Cin = 9*C, groups).  `offset`: [N][H][W][off_ld], 18 channels (dy, dx per tap).
+ */
+int tt_dcn_im2col(const float* x, const float* offset, int off_ld, float* col, int N, int H, int W, int C, int groups,
+                  tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) LiDAR branch: mmcv hard Voxelization + mmdet3d HardSimpleVFE + spconv rulebooks
+ * (lidarnet.py:87-96, cfg thinktwice.py:161-176).
+ */
+typedef struct {
+  int B, P, F;                   /* frames, points per frame, floats per point (5) */
+  float lower[3], vsize[3];
+  int grid[3];                   /* x, y, z voxel counts (672, 672, 70) */
+  int zmax;                      /* voxels with z index >= zmax are dropped (sparse_shape z = 41) */
+  int max_points, max_voxels;    /* 10, 160000 (eval) */
+  int cap;                       /* capacity of the site arrays */
+} tt_voxelize_desc;
+size_t tt_voxelize_workspace_bytes(const tt_voxelize_desc* d);
+/* feats [cap][F] = mean of the first max_points points (input order) of each voxel; coords [cap][4]
+ * (b, z, y, x); *count = number of voxels.  Site order is unspecified (results do not depend on it). */
+int tt_voxelize_mean(const tt_voxelize_desc* d, const float* points, float* feats, int* coords, int* count,
+                     void* workspace, tt_stream_t stream);
+
+typedef struct {
+  int B;
+  int in_shape[3], out_shape[3]; /* z, y, x */
+  int k[3], s[3], p[3];
+  int subm;                      /* 1: output sites = input sites */
+  int cap_in, cap_out;
+  int table_size;                /* power of two >= 2 * max(cap_in, cap_out) */
+} tt_rulebook_desc;
+size_t tt_rulebook_workspace_bytes(const tt_rulebook_desc* d);
+/* Builds out_coords/out_count (copied from the input for subm) and nbr [cap_out][kvol]
+ * (input row per tap or -1). */
+int tt_sparse_rulebook(const tt_rulebook_desc* d, const int* in_coords, const int* in_count, int* out_coords,
+                       int* out_count, int* nbr, void* workspace, tt_stream_t stream);
+/* dense()[N][C][D][H][W].view(N, C*D, H, W) (lidarnet.py:53-56) written channels-last, channel = c*D + z,
+ * with the framework's anti-transpose (framework:246) folded in when asked; `dense` must be zero-filled. */
+int tt_sparse_to_bev(const float* feats, const int* coords, const int* count, int cap, int C, int D, int H, int W,
+                     int anti_transpose, float* dense, tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (6) Look module (thinktwice_decoder.py:88-187) and multi-scale deformable attention
+ * (mmcv._ext.ms_deform_attn_forward, multi_scale_deformable_attn_function.py:72-78, 468-526).
+ */
+typedef struct {
+  int B, num_cams, num_query;    /* 4 cams, 120 look points = (T waypoints + T static points) x 15 z levels */
+  int T;                         /* pred_len (4) */
+  float img_w, img_h;
+  int levels;
+  int lvl_h[4], lvl_w[4];
+  int C;                         /* 256 channels per FPN level */
+  int q_dim;                     /* 4 + 3 + emb_dim + meas_dim + flat_dim = 519 */
+  int emb_dim, meas_dim, flat_dim;
+  int max_len_cap;               /* rows per (b, cam) in the rebatched buffers (>= num_query) */
+} tt_look_desc;
+/* thinktwice_decoder.py:155-160 + :88-114,129-137: build the look points from the current waypoints
+ * wp [B][T][2], project them into every camera (lidar2img [B][cams][16], clamp depth to 1e-5, ida
+ * [B][cams][16], normalise by the image size), validity mask, ordered compaction.
+ * Outputs: ref_cam [B][cams][Q][2], order [B][cams][Q] (compacted query ids), counts [B][cams], *max_len. */
+int tt_look_project(const tt_look_desc* d, const float* wp, const float* lidar2img, const float* ida, float* ref_cam,
+                    int* order, int* counts, int* max_len, tt_stream_t stream);
+/* thinktwice_decoder.py:117-127,140-150,161-171: rows [B*cams][cap][rows_ld] = [query | bilinear samples of the 4
+ * FPN levels at the ref point (feature index c*levels + l)], zero rows past counts; ref_rebatch [B*cams][cap][2].
+ * query = [softplus ctrl 4 | xyz 3 | temporal / static embedding | measurement feat | flattened BEV feat].
+ * mlvl: host array of 4 device pointers, each [B*cams][h][w][C] channels-last. */
+int tt_look_rebatch(const tt_look_desc* d, const float* wp, const float* ctrl_sp, const float* temporal_emb,
+                    const float* static_emb, const float* meas, const float* flat, const float* const* mlvl,
+                    const float* ref_cam, const int* order, const int* counts, float* rows, int rows_ld,
+                    float* ref_rebatch, tt_stream_t stream);
+typedef struct {
+  int BN, rows_cap, heads, levels, points, dh; /* 8 heads, 4 levels, 8 points, 32 */
+  int lvl_h[4], lvl_w[4], lvl_start[4];
+  int num_keys;
+} tt_msda_desc;
+/* value [BN][num_keys][heads*dh]; off [BN*cap][heads*levels*points*2]; logits [BN*cap][heads*levels*points];
+ * ref [BN*cap][2]; out [BN*cap][heads*dh].  Softmax over levels*points is fused. */
+int tt_msda_forward(const tt_msda_desc* d, const float* value, const float* off, const float* logits, const float* ref,
+                    const int* max_len, float* out, tt_stream_t stream);
+/* msda:338-342: zero the first B rows of every (b, cam), divide by B, sum rows < max_len -> [B][cams*C] */
+int tt_look_reduce(const float* rows, int B, int cams, int cap, int C, const int* max_len, float* out,
+                   tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (7) decoder glue
+ */
+/* GRU input plane (dense_heads/utils.py:93-104): buf[b][p][0:6] = (wp_t, softplus ctrl_t) of step t */
+int tt_gru_input(const float* wp, const float* ctrl_sp, int t, int T, float* buf, int ld, int B, int HW,
+                 tt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H_ */

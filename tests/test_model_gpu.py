@@ -1,0 +1,83 @@
+"""End-to-end parity of the B200 path against the CPU oracle on the same seeded synthetic inputs and weights.
+
+Metric: per output tensor max|x - x_ref| / max|x_ref| <= 1e-3 (BASELINE.json north_star: "within
+1e-3 relative fp32").  Stage-wise comparisons localise a failure (camera BEV, seg, LiDAR BEV, fusion, decoder)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def relerr(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def build_pair(cfg_path, B, num_points, seed=0, calib_B=None):
+    from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
+    from thinktwice_b200.config import Config
+    from thinktwice_b200.registry import build_model
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(cfg_path)
+    oracle = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'})
+    init_oracle_weights(oracle, seed)
+    batch = make_batch(cfg, B, seed=seed, num_points=num_points)
+    calibrate_bn(oracle, batch)
+    model = build_model(cfg.model)
+    model.load_state_dict(oracle.state_dict())
+    model.prepare('cuda:0')
+    return cfg, oracle, model, batch
+
+
+def compare_all(oracle, model, batch, tol=TOL):
+    keep = {}
+    with torch.no_grad():
+        ref = oracle.forward_inference(batch, keep=keep)
+    pred = model.forward_inference(batch)
+    torch.cuda.synchronize()
+    cam = model.last_cam_feat
+    errs = {}
+    errs['fpn0'] = relerr(cam['fpn_feats'][0].nchw(), keep['cam']['fpn_feats'][0])
+    errs['fpn3'] = relerr(cam['fpn_feats'][3].nchw(), keep['cam']['fpn_feats'][3])
+    errs['depth_logits'] = relerr(cam['depth'].nchw(), keep['cam']['depth'])
+    errs['seg'] = relerr(cam['seg'].nchw(), keep['cam']['seg'])
+    errs['img_feature'] = relerr(cam['img_feature'].nchw(), keep['cam_keep']['img_feature'])
+    errs['cam_bev'] = relerr(cam['bev'].nchw(), keep['cam']['bev'])
+    errs['lidar_bev'] = relerr(model.eng.bufs[[k for k in model.eng.bufs if k[0] == 'lidar.out.at'][0]].permute(0, 3, 1, 2), keep['lidar'][0])
+    for k in ('bev_feature', 'pred_speed', 'pred_features_traj', 'pred_wp', 'mu_branches', 'sigma_branches', 'future_mu',
+              'future_sigma', 'refine_flattned_BEV_feature', 'refine_BEV_feature', 'refine_future_BEV_feature'):
+        errs[k] = relerr(pred[k], ref[k])
+    print({k: f'{v:.1e}' for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, bad
+    return errs
+
+
+def test_plumbing_config_b1_matches_oracle():
+    from thinktwice_b200.config import PLUMBING_CONFIG
+    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000)
+    compare_all(oracle, model, batch)
+
+
+def test_plumbing_config_b2_keeps_batch_coupled_look_semantics():
+    """fact 4 of SURVEY.md: max_len over the batch, first B rows zeroed, divide by B — same on both sides."""
+    from thinktwice_b200.config import PLUMBING_CONFIG
+    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 2, 1500, seed=1)
+    compare_all(oracle, model, batch)
+
+
+def test_repeat_forward_is_bitwise_stable_where_deterministic():
+    from thinktwice_b200.config import PLUMBING_CONFIG
+    _, _, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000)
+    a = model.forward_inference(batch)['pred_wp'].clone()
+    b = model.forward_inference(batch)['pred_wp'].clone()
+    assert float((a - b).abs().max()) < 1e-4 * float(a.abs().max())
+
+
+def test_full_thinktwice_config_b1_matches_oracle():
+    """BASELINE.json configs[1]: thinktwice.py, 4 cams x 2 sweeps 448x896 + 40k LiDAR points, K=5, batch 1."""
+    from thinktwice_b200.config import DEFAULT_CONFIG
+    _, oracle, model, batch = build_pair(DEFAULT_CONFIG, 1, 40000)
+    compare_all(oracle, model, batch)

@@ -1,0 +1,295 @@
+// SIMT fp32 implicit-GEMM convolution / linear / sparse-conv engine (exact fp32 FFMA path).
+//
+// One kernel family serves every contraction on the path: A rows are produced on the fly either from
+// the conv geometry (dense NHWC input, zero padding, stride, dilation, groups) or from a rulebook
+// (`gather`, the sparse-conv neighbour table).  B is the pre-packed [K][Cout] weight with BatchNorm
+// folded in.  The epilogue fuses bias, up to two residuals (incl. nearest x2 up-sampled, PAFPN
+// top-down), activation, channel-offset (concat) and pixel-scatter (k2s2 transposed conv) stores.
+//
+// Tiling: BMxBNx16 per CTA, 256 threads, TMxTN register tile split into 4x4 quadrants so that
+// shared-memory reads are conflict-free 128-bit loads (A broadcast, B contiguous), global->register
+// prefetch of the next K slab overlapped with the FFMA block, double-buffered shared memory.
+#include "common.cuh"
+
+namespace {
+
+struct ConvArgs {
+  tt_conv_desc d;
+  const float* x;
+  const float* w;
+  const float* bias;
+  const float* res;
+  const float* res2;
+  const int* gather;
+  const int* m_count;
+  float* y;
+  int M, Cin_g, Cout_g, Kg, taps;
+};
+
+constexpr int BK = 16;
+
+template <int BM, int BN, int TM, int TN, bool VECA, bool VECB>
+__global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
+  constexpr int NA = BM * BK / 256;          // A floats per thread per slab (8 or 4)
+  constexpr int NB = BK * BN / 256;          // B floats per thread per slab (8 or 4)
+  constexpr int QM = TM / 4, QN = TN / 4;
+  constexpr int TX = BN / TN;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const tt_conv_desc& d = p.d;
+  const int tid = threadIdx.x;
+  const int g = blockIdx.z;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  int M = p.M;
+  if (p.m_count) M = min(M, *p.m_count);
+  if (m0 >= M) return;
+
+  // ---- A loader state: one output row per thread, NA consecutive k
+  const int a_row = tid % BM;
+  const int a_k = (tid / BM) * NA;
+  const int m = m0 + a_row;
+  const bool a_valid = m < M;
+  int an = 0, ih0 = 0, iw0 = 0;
+  if (a_valid && !p.gather) {
+    int ow = m % d.OW;
+    int t = m / d.OW;
+    int oh = t % d.OH;
+    an = t / d.OH;
+    ih0 = oh * d.stride - d.pad;
+    iw0 = ow * d.stride - d.pad;
+  }
+  const float* xg = p.x + d.x_coff + g * p.Cin_g;
+  const long long xns = d.x_nstride ? d.x_nstride : (long long)d.H * d.W * d.x_ld;
+  const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+
+  // ---- B loader state
+  constexpr int BTPR = BN / 4;               // threads per B row
+  const int b_col = (tid % BTPR) * 4;
+  const int b_k = tid / BTPR;                // rows covered per pass: 256 / BTPR
+  constexpr int BPASS = BK / (256 / BTPR);
+  static_assert(BPASS * 4 == NB, "B tiling");
+  const float* wg = p.w + g * p.Cout_g;
+
+  float ra[NA];
+  float rb[NB];
+
+  auto load_a = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < NA; j += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kg = k0 + a_k + j;
+      if (VECA) {
+        if (a_valid && kg < p.Kg) {
+          const int tap = kg / p.Cin_g;
+          const int c = kg - tap * p.Cin_g;
+          const float* src = nullptr;
+          if (p.gather) {
+            const int r = p.gather[(long long)m * p.taps + tap];
+            if (r >= 0) src = xg + (long long)r * d.x_ld + c;
+          } else {
+            const int kh = tap / d.KW, kw = tap - kh * d.KW;
+            const int ih = ih0 + kh * d.dil, iw = iw0 + kw * d.dil;
+            if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W)
+              src = xg + an * xns + ((long long)ih * d.W + iw) * d.x_ld + c;
+          }
+          if (src) v = __ldg(reinterpret_cast<const float4*>(src));
+        }
+      } else {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a_valid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = kg + i;
+            if (k < p.Kg) {
+              const int tap = k / p.Cin_g;
+              const int c = k - tap * p.Cin_g;
+              if (p.gather) {
+                const int r = p.gather[(long long)m * p.taps + tap];
+                if (r >= 0) e[i] = __ldg(xg + (long long)r * d.x_ld + c);
+              } else {
+                const int kh = tap / d.KW, kw = tap - kh * d.KW;
+                const int ih = ih0 + kh * d.dil, iw = iw0 + kw * d.dil;
+                if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W)
+                  e[i] = __ldg(xg + an * xns + ((long long)ih * d.W + iw) * d.x_ld + c);
+              }
+            }
+          }
+        }
+        v = make_float4(e[0], e[1], e[2], e[3]);
+      }
+      ra[j] = v.x; ra[j + 1] = v.y; ra[j + 2] = v.z; ra[j + 3] = v.w;
+    }
+  };
+  auto load_b = [&](int k0) {
+#pragma unroll
+    for (int ps = 0; ps < BPASS; ++ps) {
+      const int k = k0 + b_k + ps * (256 / BTPR);
+      const int n = n0 + b_col;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < p.Kg) {
+        const float* src = wg + (long long)k * d.Cout + n;
+        if (VECB) {
+          if (n < p.Cout_g) v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          if (n + 0 < p.Cout_g) v.x = __ldg(src + 0);
+          if (n + 1 < p.Cout_g) v.y = __ldg(src + 1);
+          if (n + 2 < p.Cout_g) v.z = __ldg(src + 2);
+          if (n + 3 < p.Cout_g) v.w = __ldg(src + 3);
+        }
+      }
+      rb[ps * 4 + 0] = v.x; rb[ps * 4 + 1] = v.y; rb[ps * 4 + 2] = v.z; rb[ps * 4 + 3] = v.w;
+    }
+  };
+  auto store_smem = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < NA; ++j) As[buf][a_k + j][a_row] = ra[j];
+#pragma unroll
+    for (int ps = 0; ps < BPASS; ++ps)
+      *reinterpret_cast<float4*>(&Bs[buf][b_k + ps * (256 / BTPR)][b_col]) =
+          make_float4(rb[ps * 4], rb[ps * 4 + 1], rb[ps * 4 + 2], rb[ps * 4 + 3]);
+  };
+
+  const int tx = tid % TX, ty = tid / TX;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (p.Kg + BK - 1) / BK;
+  load_a(0);
+  load_b(0);
+  store_smem(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) {
+      load_a((kt + 1) * BK);
+      load_b((kt + 1) * BK);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int q = 0; q < QM; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][q * (BM / QM) + ty * 4]);
+        a[q * 4] = v.x; a[q * 4 + 1] = v.y; a[q * 4 + 2] = v.z; a[q * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int q = 0; q < QN; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][q * (BN / QN) + tx * 4]);
+        b[q * 4] = v.x; b[q * 4 + 1] = v.y; b[q * 4 + 2] = v.z; b[q * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_smem(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue
+  const bool vec_out = VECB && (d.y_ld % 4 == 0) && (d.y_coff % 4 == 0) &&
+                       (p.res == nullptr || (d.res_ld % 4 == 0 && d.res_coff % 4 == 0)) &&
+                       (p.res2 == nullptr || (d.res2_ld % 4 == 0 && d.res2_coff % 4 == 0));
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int row = m0 + (i / 4) * (BM / QM) + ty * 4 + (i % 4);
+    if (row >= M) continue;
+    long long yoff, rpix = row, r1pix = row;
+    if (p.gather) {
+      yoff = (long long)row * d.y_ld;
+    } else {
+      const int ow = row % d.OW;
+      const int t = row / d.OW;
+      const int oh = t % d.OH;
+      const int n = t / d.OH;
+      yoff = n * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
+      if (d.res_mode == TT_RES_UP2_NEAREST) {
+        const int rh = (oh * d.res_H) / d.OH, rw = (ow * d.res_W) / d.OW;
+        r1pix = ((long long)n * d.res_H + rh) * d.res_W + rw;
+      }
+    }
+    float* yrow = p.y + yoff + d.y_coff + g * p.Cout_g;
+    const float* r1 = p.res ? p.res + r1pix * d.res_ld + d.res_coff + g * p.Cout_g : nullptr;
+    const float* r2 = p.res2 ? p.res2 + rpix * d.res2_ld + d.res2_coff + g * p.Cout_g : nullptr;
+    const float* bs = p.bias ? p.bias + g * p.Cout_g : nullptr;
+#pragma unroll
+    for (int q = 0; q < QN; ++q) {
+      const int col = n0 + q * (BN / QN) + tx * 4;
+      if (col >= p.Cout_g) continue;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = acc[i][q * 4 + j];
+      if (vec_out) {
+        if (bs) { const float4 t = __ldg(reinterpret_cast<const float4*>(bs + col)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+        if (r1) { const float4 t = *reinterpret_cast<const float4*>(r1 + col); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+        if (r2) { const float4 t = *reinterpret_cast<const float4*>(r2 + col); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+        *reinterpret_cast<float4*>(yrow + col) =
+            make_float4(tt_act(v[0], d.act), tt_act(v[1], d.act), tt_act(v[2], d.act), tt_act(v[3], d.act));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (col + j < p.Cout_g) {
+            float t = v[j];
+            if (bs) t += __ldg(bs + col + j);
+            if (r1) t += r1[col + j];
+            if (r2) t += r2[col + j];
+            yrow[col + j] = tt_act(t, d.act);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+void launch_cfg(const ConvArgs& a, bool veca, bool vecb, cudaStream_t st) {
+  dim3 grid(tt_cdiv(a.M, BM), tt_cdiv(a.Cout_g, BN), a.d.groups);
+  if (veca && vecb) conv_igemm_simt<BM, BN, TM, TN, true, true><<<grid, 256, 0, st>>>(a);
+  else if (veca) conv_igemm_simt<BM, BN, TM, TN, true, false><<<grid, 256, 0, st>>>(a);
+  else if (vecb) conv_igemm_simt<BM, BN, TM, TN, false, true><<<grid, 256, 0, st>>>(a);
+  else conv_igemm_simt<BM, BN, TM, TN, false, false><<<grid, 256, 0, st>>>(a);
+}
+
+}  // namespace
+
+extern long long g_tt_launches;
+
+int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
+                   const float* res2, const int* gather, const int* m_count, float* y, cudaStream_t st) {
+  ConvArgs a;
+  a.d = *d;
+  a.x = x; a.w = w; a.bias = bias; a.res = res; a.res2 = res2; a.gather = gather; a.m_count = m_count; a.y = y;
+  a.Cin_g = d->Cin / d->groups;
+  a.Cout_g = d->Cout / d->groups;
+  if (gather) {
+    a.taps = d->taps;
+    a.M = d->M;
+  } else {
+    a.taps = d->KH * d->KW;
+    a.M = d->N * d->OH * d->OW;
+  }
+  a.Kg = a.taps * a.Cin_g;
+  if (a.M <= 0) return TT_OK;
+  const bool veca = (a.Cin_g % 4 == 0) && (d->x_ld % 4 == 0) && (d->x_coff % 4 == 0) && (d->x_nstride % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const bool vecb = (a.Cout_g % 4 == 0) && (d->Cout % 4 == 0) && (d->y_nstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
+                    (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                    (res == nullptr || (reinterpret_cast<uintptr_t>(res) & 15) == 0) &&
+                    (res2 == nullptr || (reinterpret_cast<uintptr_t>(res2) & 15) == 0);
+  // tile choice: big tiles when they still fill the 148 SMs, otherwise smaller ones
+  const long long big = (long long)tt_cdiv(a.M, 128) * tt_cdiv(a.Cout_g, 128) * d->groups;
+  if (a.Cout_g > 64 && big >= 148) launch_cfg<128, 128, 8, 8>(a, veca, vecb, st);
+  else if (a.Cout_g <= 64 && (long long)tt_cdiv(a.M, 128) * d->groups >= 148) launch_cfg<128, 64, 8, 4>(a, veca, vecb, st);
+  else launch_cfg<64, 64, 4, 4>(a, veca, vecb, st);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_conv2d(simt)");
+  return TT_OK;
+}

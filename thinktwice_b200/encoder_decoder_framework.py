@@ -1,0 +1,222 @@
+"""EncoderDecoder — the model entry point, B200-native.
+
+Drop-in for the reference class of the same name (open_loop_training/code/encoder_decoder_framework.py):
+same registry name, same constructor keywords, same `forward_inference(batch)` / `process_action` /
+`control_pid` signatures and the same pred dict, so `leaderboard/team_code/thinktwice_agent.py:456-461`
+calls it unchanged.  The forward runs entirely in libtt_b200 (no eager / CPU fallback).
+"""
+from collections import deque
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib
+from .engine import Engine, FMap
+from .lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
+from .params import ParamTree, param_spec
+from .registry import DETECTORS, build_backbone, build_head
+from .weights import Packer, bn_affine
+from . import lss as _lss, lidarnet as _lidarnet, thinktwice_decoder as _decoder  # noqa: F401  (registers the modules)
+
+
+class PIDController:
+    """code/utils.py:7-29 (host-side, stateful)."""
+
+    def __init__(self, K_P=1.0, K_I=0.0, K_D=0.0, n=20):
+        self._K_P, self._K_I, self._K_D = K_P, K_I, K_D
+        self._window = deque([0 for _ in range(n)], maxlen=n)
+        self._max = 0.0
+        self._min = 0.0
+
+    def step(self, error):
+        self._window.append(error)
+        self._max = max(self._max, abs(error))
+        self._min = -abs(self._max)
+        if len(self._window) >= 2:
+            integral = np.mean(self._window)
+            derivative = self._window[-1] - self._window[-2]
+        else:
+            integral = derivative = 0.0
+        return self._K_P * error + self._K_I * integral + self._K_D * derivative
+
+
+@DETECTORS.register_module()
+class EncoderDecoder(nn.Module):
+    def __init__(self, img_encoder, decoder, lidar_encoder=None, num_cams=4, use_depth=False, use_seg=False,
+                 downsample_factor=16, seg_downsample_factor=2, train_cfg=None, test_cfg=None, seed=0):
+        super().__init__()
+        self.config = train_cfg
+        self.num_cams = num_cams
+        self.model_cfg = dict(img_encoder=img_encoder, decoder=decoder, lidar_encoder=lidar_encoder)
+        self.turn_controller = PIDController(K_P=train_cfg['turn_KP'], K_I=train_cfg['turn_KI'], K_D=train_cfg['turn_KD'], n=train_cfg['turn_n'])
+        self.speed_controller = PIDController(K_P=train_cfg['speed_KP'], K_I=train_cfg['speed_KI'], K_D=train_cfg['speed_KD'], n=train_cfg['speed_n'])
+        self.img_encoder = build_backbone(img_encoder)
+        self.lidar_encoder = build_backbone(lidar_encoder)
+        self.decoder = build_head(decoder)
+        self.dbound = self.img_encoder.d_bound
+        # parameters / buffers in the reference's state_dict naming (checkpoint-compatible)
+        self.params = ParamTree(param_spec(self.model_cfg), seed=seed)
+        for k, v in self.img_encoder.buffers().items():
+            getattr(self.params.img_encoder, k).copy_(v)
+        self.eng = None
+
+    # state_dict of the model == state_dict of the parameter tree (reference key names, no prefix)
+    def state_dict(self, *a, **k):
+        return self.params.state_dict(*a, **k)
+
+    def load_state_dict(self, sd, strict=True):
+        r = self.params.load_state_dict(sd, strict=strict)
+        self.eng = None                                            # weights must be re-packed
+        return r
+
+    # ------------------------------------------------------------------ weight preparation
+    def prepare(self, device='cuda:0', impl=lib.IMPL_AUTO):
+        dev = torch.device(device)
+        lib.require_cuda(dev)
+        self.eng = e = Engine(dev, impl)
+        pk = Packer(self.params.state_dict(), dev)
+        self.img_encoder.prepare(pk, e)
+        self.lidar_encoder.prepare(pk, e)
+        self.decoder.prepare(pk, e, self)
+        w = self.w = {}
+        for n in ('conv_cam', 'conv_lidar', 'conv_fusion'):
+            w[n] = (pk.conv(n + '.0', bn=n + '.1'), pk.conv(n + '.3', bn=n + '.4'))
+        w['to32'] = pk.conv('_256_to_32')
+        for n in ('MLP21', 'MLP10', 'MLP4', 'MLP2'):
+            w[n] = dict(c1=pk.conv(n + '.conv1', bn=n + '.bn1'), c2=pk.conv(n + '.conv2', bn=n + '.bn2'),
+                        f1=pk.conv1x1_as_linear(n + '.se.fc1'), f2=pk.conv1x1_as_linear(n + '.se.fc2'))
+        w['conv21_10'], w['conv10_4'], w['conv4_2'] = pk.conv('conv21_10'), pk.conv('conv10_4'), pk.conv('conv4_2')
+        # output_fc flattens an NCHW (256, 2, 2) map (framework:234): re-index the columns for channels-last
+        idx = [c * 4 + p for p in range(4) for c in range(256)]
+        w['fc0'] = pk.linear('output_fc.0', cin_index=idx)
+        w['fc3'] = pk.linear('output_fc.3', in_affine=bn_affine(pk.sd, 'output_fc.2', 1e-5))   # BN1d after ReLU folds forward
+        w['meas0'], w['meas2'] = pk.linear('measurements_encoder.0', cin_pad=12), pk.linear('measurements_encoder.2')
+        return self
+
+    # ------------------------------------------------------------------ shared pyramid (framework:224-234, decoder grid2feat)
+    def se_block(self, x, wb, tag, out=None):
+        e = self.eng
+        y = e.conv(x, wb['c1'], name=tag + '.y1', pad=1, act=ACT_RELU)
+        y = e.conv(y, wb['c2'], name=tag + '.y2', pad=1, act=ACT_RELU)
+        s = e.se_pool(y, tag + '.s')
+        g = e.linear(e.linear(s, wb['f1'], name=tag + '.g1', act=ACT_RELU), wb['f2'], name=tag + '.g2')
+        return e.se_apply(y, g, x, out=out, name=tag + '.out')
+
+    def pyramid(self, f21, tag):
+        """(N, 21, 21, 32) -> flattened (N, 256) feature and the mid maps."""
+        e, w = self.eng, self.w
+        f10 = self.se_block(e.conv(f21, w['conv21_10'], name=tag + '.c10', stride=2, act=ACT_RELU), w['MLP10'], tag + '.m10')
+        f4 = self.se_block(e.conv(f10, w['conv10_4'], name=tag + '.c4', stride=2, act=ACT_RELU), w['MLP4'], tag + '.m4')
+        f2 = self.se_block(e.conv(f4, w['conv4_2'], name=tag + '.c2', act=ACT_RELU), w['MLP2'], tag + '.m2')
+        flat_in = FMap(f2.t, f2.N, 1, 1, f2.H * f2.W * f2.C)           # channels-last flatten (weights re-indexed)
+        h = e.linear(flat_in, w['fc0'], name=tag + '.fc0', act=ACT_RELU)
+        return e.linear(h, w['fc3'], name=tag + '.flat', act=ACT_RELU), [f10, f4, f2]
+
+    def get_fusion_feat(self, cam_bev, lidar_feat):                # framework:213-235
+        e, w = self.eng, self.w
+        t = e.conv(cam_bev, w['conv_cam'][0], name='fu.cam1', pad=1, act=ACT_RELU)
+        cam = e.conv(t, w['conv_cam'][1], name='fu.cam', pad=1, act=ACT_RELU, res=cam_bev)
+        cat = e.fmap('fu.cat', cam.N, cam.H, cam.W, 512)
+        e.copy_cols(cam, cat.slice(0, 256))
+        t = e.conv(lidar_feat, w['conv_lidar'][0], name='fu.pts1', stride=2, pad=1, act=ACT_RELU)
+        pts = e.conv(t, w['conv_lidar'][1], out=cat.slice(256, 256), name='fu.pts', stride=2, pad=1, act=ACT_RELU)
+        t = e.conv(cat, w['conv_fusion'][0], name='fu.f1', pad=1, act=ACT_RELU)
+        bev = e.conv(t, w['conv_fusion'][1], name='fu.bev', pad=1, act=ACT_RELU, res=cam, res2=pts)
+        f21 = self.se_block(e.conv(bev, w['to32'], name='fu.to32', pad=1, act=ACT_RELU), w['MLP21'], 'fu.m21')
+        flat, mids = self.pyramid(f21, 'fu.py')
+        return flat, f21, [None, None, f21] + mids, lidar_feat
+
+    # ------------------------------------------------------------------ forward (framework:194-210, 238-250)
+    def extract_sensor_feat(self, img, state, img_metas, points):
+        e = self.eng
+        cam = self.img_encoder(img=img, img_metas=img_metas)
+        cam['bev'] = e.anti_transpose(cam['bev'], 'cam.bev.at')     # rot90(flip): match the Roach BEV
+        st = torch.cat(state[:3], dim=-1).float()
+        st = torch.cat([st, st.new_zeros(st.shape[0], 3)], 1).contiguous()
+        m = e.linear(e.wrap(st.view(-1, 1, 1, 12)), self.w['meas0'], name='meas.h', act=ACT_RELU)
+        meas = e.linear(m, self.w['meas2'], name='meas', act=ACT_RELU)
+        lidar = self.lidar_encoder(points[:, -1, ...])
+        return cam, lidar, meas
+
+    @torch.no_grad()
+    def forward_inference(self, batch):
+        if self.eng is None:
+            self.prepare(batch['img'].device)
+        dev = self.eng.device
+        self.epoch = 10000
+        target_point = batch['target_point'].to(dev, dtype=torch.float32)
+        command = batch['target_command'].to(dev, dtype=torch.float32)
+        speed = batch['speed'].to(dev, dtype=torch.float32).view(-1, 1) / 12.
+        state = [speed, target_point, command, batch.get('target_command_raw')]
+        cam, lidar, meas = self.extract_sensor_feat(batch['img'].to(dev), state, batch['img_metas'], batch['points'].to(dev))
+        flat, bev32, mid, lidar_hi = self.get_fusion_feat(cam['bev'], lidar[0])
+        pred = self.decoder(flat, bev32, meas, target_point, self, None,
+                            [cam['lidar2img'], cam['ida_mat'], cam['fpn_feats'], lidar_hi])
+        self.last_cam_feat = cam                                   # cam['seg'] etc. for parity checks
+        return pred
+
+    def forward(self, is_eval=True, **kwargs):
+        raise NotImplementedError('training / loss path is out of scope (SURVEY.md §8f f4); use forward_inference')
+
+    # ------------------------------------------------------------------ host post-processing (framework:268-390)
+    @staticmethod
+    def _get_action_beta(alpha, beta):
+        x = torch.zeros_like(alpha)
+        x[:, 1] += 0.5
+        m1 = (alpha > 1) & (beta > 1)
+        x[m1] = (alpha[m1] - 1) / (alpha[m1] + beta[m1] - 2)
+        x[(alpha <= 1) & (beta > 1)] = 0.0
+        x[(alpha > 1) & (beta <= 1)] = 1.0
+        m4 = (alpha <= 1) & (beta <= 1)
+        x[m4] = alpha[m4] / torch.clamp(alpha[m4] + beta[m4], min=1e-5)
+        return x * 2 - 1
+
+    def process_action(self, pred, command, speed, target_point):
+        action = self._get_action_beta(pred['mu_branches'][:, -1, :].view(1, 2), pred['sigma_branches'][:, -1, :].view(1, 2))
+        acc, steer = action.cpu().numpy()[0].astype(np.float64)
+        throttle, brake = (acc, 0.0) if acc >= 0.0 else (0.0, np.abs(acc))
+        throttle, steer, brake = np.clip(throttle, 0, 1), np.clip(steer, -1, 1), np.clip(brake, 0, 1)
+        metadata = {'speed': float(speed.cpu().numpy().astype(np.float64)), 'steer': float(steer), 'throttle': float(throttle),
+                    'brake': float(brake), 'command': command, 'target_point': target_point}
+        return steer, throttle, brake, metadata
+
+    def control_pid(self, waypoints, velocity, target, stuck_desired_speed=-1):
+        assert waypoints.size(0) == 1
+        cfg = self.config
+        waypoints = waypoints[0].data.cpu().numpy()
+        saved_waypoints, saved_target = waypoints.copy(), target.copy()
+        waypoints, target = waypoints[:, ::-1], target[::-1]
+        num_pairs = len(waypoints) - 1
+        best_norm, desired_speed, aim = 1e5, 0, waypoints[0]
+        for i in range(num_pairs):
+            desired_speed += np.linalg.norm(waypoints[i + 1] - waypoints[i]) * 2.0 / num_pairs
+            norm = np.linalg.norm((waypoints[i + 1] + waypoints[i]) / 2.0)
+            if abs(cfg['aim_dist'] - best_norm) > abs(cfg['aim_dist'] - norm):
+                aim, best_norm = waypoints[i], norm
+        desired_speed = desired_speed.astype(np.float64)
+        if stuck_desired_speed > 0:
+            desired_speed = stuck_desired_speed
+        aim_last = waypoints[-1] - waypoints[-2]
+        angle = np.degrees(np.pi / 2 - np.arctan2(aim[1], aim[0])) / 90
+        angle_last = np.degrees(np.pi / 2 - np.arctan2(aim_last[1], aim_last[0])) / 90
+        angle_target = np.degrees(np.pi / 2 - np.arctan2(target[1], target[0])) / 90
+        use_target = np.abs(angle_target) < np.abs(angle)
+        use_target = use_target or (np.abs(angle_target - angle_last) > cfg['angle_thresh'] and target[1] < cfg['dist_thresh'])
+        angle_final = (angle_target if use_target else angle).astype(np.float64)
+        speed = velocity[0].data.cpu().numpy()
+        if speed < 0.01:
+            angle_final = 0.0
+        steer = np.clip(self.turn_controller.step(angle_final), -1.0, 1.0)
+        brake = desired_speed < cfg['brake_speed'] or (speed / desired_speed) > cfg['brake_ratio']
+        delta = np.clip(desired_speed - speed, 0.0, cfg['clip_delta'])
+        throttle = np.clip(self.speed_controller.step(delta), 0.0, 1.0)
+        throttle = throttle if not brake else 0.0
+        metadata = {'speed': float(speed.astype(np.float64)), 'steer': float(steer), 'throttle': float(throttle), 'brake': float(brake),
+                    'wp_4': tuple(saved_waypoints[3].astype(np.float64)), 'wp_3': tuple(saved_waypoints[2].astype(np.float64)),
+                    'wp_2': tuple(saved_waypoints[1].astype(np.float64)), 'wp_1': tuple(saved_waypoints[0].astype(np.float64)),
+                    'aim': tuple(aim.astype(np.float64)), 'target': tuple(saved_target.astype(np.float64)),
+                    'desired_speed': float(desired_speed), 'angle': float(angle.astype(np.float64)),
+                    'angle_last': float(angle_last.astype(np.float64)), 'angle_target': float(angle_target.astype(np.float64)),
+                    'angle_final': float(angle_final), 'delta': float(delta.astype(np.float64))}
+        return steer, throttle, brake, metadata

@@ -1,0 +1,226 @@
+"""Host-side op layer: channels-last feature-map handles, a persistent buffer arena and one Python
+method per C-ABI op.  No arithmetic happens here — every method ends in a libtt_b200 call.
+
+Buffers are allocated once per (name, shape) and reused on every forward, so a steady-state forward
+performs no allocation (CUDA-graph capturable) and keeps activations resident in HBM.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib
+from .lib import ConvDesc, _p, _stream
+
+
+class FMap:
+    """A logical (N, H, W, C) fp32 tensor stored channels-last inside a buffer whose pixels hold `ld`
+    floats; the C channels start at `coff`.  Concat = several FMaps viewing one buffer."""
+    __slots__ = ('t', 'N', 'H', 'W', 'C', 'ld', 'coff')
+
+    def __init__(self, t, N, H, W, C, ld=None, coff=0):
+        self.t, self.N, self.H, self.W, self.C = t, N, H, W, C
+        self.ld = ld if ld is not None else C
+        self.coff = coff
+
+    def slice(self, coff, C):
+        return FMap(self.t, self.N, self.H, self.W, C, self.ld, self.coff + coff)
+
+    def rows(self):
+        return self.N * self.H * self.W
+
+    def as_rows(self):
+        """view as a (rows, 1, 1, C) map (for Linear layers)."""
+        return FMap(self.t, self.rows(), 1, 1, self.C, self.ld, self.coff)
+
+    def dense(self):
+        """contiguous (N, H, W, C) torch view/copy of the logical tensor (debug / tests / outputs)."""
+        v = self.t.view(self.N, self.H, self.W, self.ld)[..., self.coff:self.coff + self.C]
+        return v
+
+    def nchw(self):
+        return self.dense().permute(0, 3, 1, 2)
+
+
+class PackedConv:
+    """weights of one conv / linear in kernel layout: w [taps*Cin_g][Cout] (BatchNorm folded), bias [Cout]|None."""
+    __slots__ = ('w', 'bias', 'Cin', 'Cout', 'KH', 'KW', 'groups')
+
+    def __init__(self, w, bias, Cin, Cout, KH=1, KW=1, groups=1):
+        self.w, self.bias, self.Cin, self.Cout, self.KH, self.KW, self.groups = w, bias, Cin, Cout, KH, KW, groups
+
+
+class Engine:
+    def __init__(self, device, impl=lib.IMPL_AUTO):
+        self.device = torch.device(device)
+        self.impl = impl
+        self.bufs = {}
+        lib.load()
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, name, shape, dtype=torch.float32, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t
+
+    def fmap(self, name, N, H, W, C, ld=None, zero=False):
+        ld = ld if ld is not None else C
+        return FMap(self.buf(name, (N, H, W, ld), zero=zero), N, H, W, C, ld, 0)
+
+    def wrap(self, t, C=None):
+        """wrap an existing contiguous (N, H, W, ld) tensor."""
+        N, H, W, ld = t.shape
+        return FMap(t, N, H, W, C if C is not None else ld, ld, 0)
+
+    # ------------------------------------------------------------------ conv / linear
+    def conv(self, x, pw, out=None, name=None, stride=1, pad=0, dil=1, act=0, res=None, res_mode=0, res2=None,
+             scatter=None, out_ld=None, impl=None, x_nstride=0, y_nstride=0, n_images=None):
+        """y = act(conv(x) + bias + res + res2).  `out` (FMap) selects the destination (concat slice / scatter
+        target); otherwise a buffer `name` is created.  scatter = (oy_mul, oy_add, ox_mul, ox_add)."""
+        assert x.C == pw.Cin, (x.C, pw.Cin, name)
+        OH = (x.H + 2 * pad - dil * (pw.KH - 1) - 1) // stride + 1
+        OW = (x.W + 2 * pad - dil * (pw.KW - 1) - 1) // stride + 1
+        if out is None:
+            out = self.fmap(name, x.N, OH, OW, pw.Cout, out_ld)
+        d = ConvDesc()
+        d.N, d.H, d.W, d.Cin, d.x_ld, d.x_coff = (n_images or x.N), x.H, x.W, x.C, x.ld, 0
+        d.x_nstride, d.y_nstride = x_nstride, y_nstride
+        d.Cout, d.KH, d.KW, d.stride, d.pad, d.dil, d.groups = pw.Cout, pw.KH, pw.KW, stride, pad, dil, pw.groups
+        d.OH, d.OW = OH, OW
+        d.y_ld, d.y_coff, d.yH, d.yW = out.ld, 0, out.H, out.W
+        if scatter is None:
+            assert out.H == OH and out.W == OW and out.C == pw.Cout, (name, out.H, OH, out.W, OW)
+            d.oy_mul, d.oy_add, d.ox_mul, d.ox_add = 1, 0, 1, 0
+        else:
+            d.oy_mul, d.oy_add, d.ox_mul, d.ox_add = scatter
+        d.act = act
+        d.res_mode = res_mode if res is not None else 0
+        if res is not None:
+            if d.res_mode == 0:
+                d.res_mode = lib.RES_SAME
+            d.res_ld, d.res_coff, d.res_H, d.res_W = res.ld, 0, res.H, res.W
+            assert res.C == pw.Cout
+        if res2 is not None:
+            d.res2_ld, d.res2_coff = res2.ld, 0
+        d.impl = self.impl if impl is None else impl
+        lib.check(lib.load().tt_conv2d(
+            C.byref(d), _p(x.t, x.coff), _p(pw.w), _p(pw.bias),
+            _p(res.t, res.coff) if res is not None else None, _p(res2.t, res2.coff) if res2 is not None else None,
+            None, None, _p(out.t, out.coff), _stream()), f'tt_conv2d[{name}]')
+        return out
+
+    def linear(self, x, pw, out=None, name=None, act=0, res=None):
+        """x: FMap with H=W=1 (rows in N) or any FMap (flattened over pixels)."""
+        xr = x.as_rows()
+        if out is None:
+            out = self.fmap(name, xr.N, 1, 1, pw.Cout)
+        else:
+            out = out.as_rows()
+        return self.conv(xr, pw, out=out, name=name, act=act, res=res.as_rows() if res is not None else None)
+
+    def sparse_conv(self, feats, pw, nbr, count, cap, taps, out, act=0, res=None, name=None):
+        """gather-mode GEMM: feats [cap_in][Cin] tensor, nbr [cap][taps] int32, count device int, out [cap][Cout]."""
+        d = ConvDesc()
+        d.N, d.H, d.W, d.Cin, d.x_ld, d.x_coff = 1, 1, 1, pw.Cin, feats.shape[1], 0
+        d.Cout, d.KH, d.KW, d.stride, d.pad, d.dil, d.groups = pw.Cout, 1, 1, 1, 0, 1, 1
+        d.OH, d.OW, d.y_ld, d.y_coff, d.yH, d.yW = 1, 1, out.shape[1], 0, 1, 1
+        d.oy_mul, d.oy_add, d.ox_mul, d.ox_add = 1, 0, 1, 0
+        d.act = act
+        if res is not None:
+            d.res_mode, d.res_ld = lib.RES_SAME, res.shape[1]
+        d.taps, d.M = taps, cap
+        d.impl = lib.IMPL_SIMT
+        lib.check(lib.load().tt_conv2d(C.byref(d), _p(feats), _p(pw.w), _p(pw.bias), _p(res), None, _p(nbr), _p(count),
+                                       _p(out), _stream()), f'tt_conv2d[sparse {name}]')
+        return out
+
+    # ------------------------------------------------------------------ memory-bound ops
+    def nchw_to_nhwc(self, x, name, cpad=None):
+        N, Cc, H, W = x.shape
+        cpad = cpad or Cc
+        out = self.fmap(name, N, H, W, cpad)
+        lib.call('tt_nchw_to_nhwc', _p(x), _p(out.t), N, Cc, H, W, out.ld, 0, cpad)
+        return out
+
+    def nhwc_to_nchw(self, x, name):
+        out = self.buf(name, (x.N, x.C, x.H, x.W))
+        lib.call('tt_nhwc_to_nchw', _p(x.t, x.coff), x.ld, 0, _p(out), x.N, x.C, x.H, x.W)
+        return out
+
+    def maxpool3x3s2(self, x, name):
+        assert x.ld == x.C and x.coff == 0
+        out = self.fmap(name, x.N, (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1, x.C)
+        lib.call('tt_maxpool3x3s2', _p(x.t), _p(out.t), x.N, x.H, x.W, x.C)
+        return out
+
+    def upsample2x(self, x, name):
+        assert x.ld == x.C and x.coff == 0
+        out = self.fmap(name, x.N, 2 * x.H, 2 * x.W, x.C)
+        lib.call('tt_upsample2x_bilinear_ac', _p(x.t), _p(out.t), x.N, x.H, x.W, x.C)
+        return out
+
+    def global_avgpool(self, x, name):
+        out = self.fmap(name, x.N, 1, 1, x.C)
+        lib.call('tt_global_avgpool', _p(x.t, x.coff), x.ld, 0, _p(out.t), x.N, x.H * x.W, x.C)
+        return out
+
+    def broadcast_rows(self, v, out):
+        lib.call('tt_broadcast_rows', _p(v.t, v.coff), _p(out.t, out.coff), out.N, out.H * out.W, out.C, out.ld, 0)
+        return out
+
+    def se_gate(self, x, g, name):
+        assert x.ld == x.C and x.coff == 0 and g.ld == g.C
+        out = self.fmap(name, x.N, x.H, x.W, x.C)
+        lib.call('tt_se_gate', _p(x.t), _p(g.t), _p(out.t), x.N, x.H * x.W, x.C)
+        return out
+
+    def se_pool(self, x, name):
+        assert x.ld == x.C and x.coff == 0
+        out = self.fmap(name, x.N, 1, 1, x.C)
+        lib.call('tt_se_pool', _p(x.t), _p(out.t), x.N, x.H * x.W, x.C)
+        return out
+
+    def se_apply(self, x, g, shortcut, out=None, name=None):
+        assert x.ld == x.C and x.coff == 0
+        if out is None:
+            out = self.fmap(name, x.N, x.H, x.W, x.C)
+        lib.call('tt_se_apply', _p(x.t), _p(g.t), _p(shortcut.t, shortcut.coff), shortcut.ld, 0, _p(out.t, out.coff),
+                 out.ld, 0, x.N, x.H * x.W, x.C)
+        return out
+
+    def anti_transpose(self, x, name):
+        assert x.ld == x.C and x.coff == 0 and x.H == x.W
+        out = self.fmap(name, x.N, x.H, x.W, x.C)
+        lib.call('tt_anti_transpose', _p(x.t), _p(out.t), x.N, x.H, x.C)
+        return out
+
+    def copy_cols(self, src, dst, rdiv=1, rmod=None):
+        """dst rows r (all pixels of dst) <- src row (r // rdiv) % rmod; copies src.C columns."""
+        rows = dst.rows()
+        rmod = rmod if rmod is not None else max(src.rows(), 1)
+        assert src.C == dst.C
+        lib.call('tt_copy2d', _p(src.t, src.coff), src.ld, _p(dst.t, dst.coff), dst.ld, rows, src.C, rdiv, rmod)
+        return dst
+
+    def layernorm(self, x, gamma, beta, out=None, name=None, out_ld=None, row_count=None):
+        xr = x.as_rows()
+        if out is None:
+            out = self.fmap(name, xr.N, 1, 1, xr.C, out_ld, zero=True)
+        lib.call('tt_layernorm', _p(xr.t, xr.coff), xr.ld, _p(gamma), _p(beta), _p(out.t, out.coff), out.ld, xr.N, xr.C,
+                 _p(row_count))
+        return out
+
+    def eltwise(self, op, a, b=None, c=None, out=None, name=None, act=0):
+        a_, b_, c_ = a.as_rows(), (b.as_rows() if b is not None else None), (c.as_rows() if c is not None else None)
+        if out is None:
+            out = self.fmap(name, a.N, a.H, a.W, a.C)
+        o_ = out.as_rows()
+        lib.call('tt_eltwise', op, act, _p(a_.t, a_.coff), a_.ld, _p(b_.t, b_.coff) if b_ else None, b_.ld if b_ else 0,
+                 _p(c_.t, c_.coff) if c_ else None, c_.ld if c_ else 0, _p(o_.t, o_.coff), o_.ld, a_.N, a_.C)
+        return out
+
+    def fill(self, t, v=0.0):
+        lib.call('tt_fill', _p(t), C.c_float(v), C.c_longlong(t.numel()))
+        return t

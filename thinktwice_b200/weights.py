@@ -1,0 +1,104 @@
+"""Weight preparation: reference-format state_dict -> kernel-layout tensors on the device.
+
+Done once at load time (eval mode): BatchNorm running statistics are folded into the preceding (or, for
+BN-after-ReLU, the following) linear map, weights are repacked K-major as [taps*Cin_g][Cout] for the
+implicit-GEMM kernels, and transposed convolutions are split into their four 1x1 phases.
+"""
+import torch
+
+from .engine import PackedConv
+
+
+def bn_affine(sd, n, eps):
+    s = sd[n + '.weight'].double() / torch.sqrt(sd[n + '.running_var'].double() + eps)
+    t = sd[n + '.bias'].double() - sd[n + '.running_mean'].double() * s
+    return s, t
+
+
+class Packer:
+    def __init__(self, sd, device):
+        self.sd = {k: v.detach().cpu() for k, v in sd.items()}
+        self.device = device
+
+    def _dev(self, t):
+        return None if t is None else t.float().contiguous().to(self.device)
+
+    @staticmethod
+    def _reindex(w, index):
+        """input-channel gather along dim 1; index -1 inserts a zero channel."""
+        idx = torch.as_tensor(index, dtype=torch.long)
+        out = w.new_zeros((w.shape[0], idx.numel()) + tuple(w.shape[2:]))
+        ok = idx >= 0
+        out[:, ok] = w[:, idx[ok]]
+        return out
+
+    def conv(self, n, bn=None, eps=1e-5, groups=1, cin_pad=None, cin_index=None):
+        """Conv2d weight (Cout, Cin_g, KH, KW) [+bias] followed by BN `bn` -> PackedConv."""
+        w = self.sd[n + '.weight'].double()
+        b = self.sd.get(n + '.bias')
+        b = b.double() if b is not None else None
+        if bn is not None:
+            s, t = bn_affine(self.sd, bn, eps)
+            w = w * s.view(-1, 1, 1, 1)
+            b = t if b is None else b * s + t
+        if cin_index is not None:
+            w = self._reindex(w, cin_index)
+        Cout, Cg, KH, KW = w.shape
+        if cin_pad is not None and cin_pad > Cg:
+            assert groups == 1
+            w = torch.cat([w, w.new_zeros(Cout, cin_pad - Cg, KH, KW)], 1)
+            Cg = cin_pad
+        packed = w.permute(2, 3, 1, 0).reshape(KH * KW * Cg, Cout)
+        return PackedConv(self._dev(packed), self._dev(b), Cg * groups, Cout, KH, KW, groups)
+
+    def linear(self, n, bn_after=None, eps=1e-5, in_affine=None, cin_pad=None, weight=None, bias=None, cin_index=None):
+        """Linear (Cout, Cin).  in_affine=(s, t): the input is s*x + t (a folded BatchNorm1d in front);
+        bn_after: BatchNorm1d applied to the output."""
+        w = (self.sd[n + '.weight'] if weight is None else weight).double()
+        b = self.sd.get(n + '.bias') if bias is None else bias
+        b = b.double() if b is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+        if in_affine is not None:
+            s, t = in_affine
+            b = b + w @ t
+            w = w * s.view(1, -1)
+        if bn_after is not None:
+            s, t = bn_affine(self.sd, bn_after, eps)
+            w = w * s.view(-1, 1)
+            b = b * s + t
+        if cin_index is not None:
+            w = self._reindex(w, cin_index)
+        Cout, Cin = w.shape
+        if cin_pad is not None and cin_pad > Cin:
+            w = torch.cat([w, w.new_zeros(Cout, cin_pad - Cin)], 1)
+            Cin = cin_pad
+        return PackedConv(self._dev(w.t()), self._dev(b), Cin, Cout)
+
+    def conv1x1_as_linear(self, n, **kw):
+        w = self.sd[n + '.weight']
+        return self.linear(n, weight=w.reshape(w.shape[0], -1), **kw)
+
+    def convT(self, n, bn=None, eps=1e-5):
+        """ConvTranspose2d k2s2 (Cin, Cout, 2, 2) -> four PackedConv, phase (i, j) writes pixel (2h+i, 2w+j)."""
+        w = self.sd[n + '.weight'].double()
+        b = self.sd.get(n + '.bias')
+        b = b.double() if b is not None else None
+        if bn is not None:
+            s, t = bn_affine(self.sd, bn, eps)
+            w = w * s.view(1, -1, 1, 1)
+            b = t if b is None else b * s + t
+        Cin, Cout = w.shape[:2]
+        bd = self._dev(b)
+        return [[PackedConv(self._dev(w[:, :, i, j]), bd, Cin, Cout) for j in range(2)] for i in range(2)]
+
+    def spconv(self, n, bn, eps=1e-3):
+        """spconv weight (Cout, kd, kh, kw, Cin) + BatchNorm1d -> PackedConv with K = (tap, cin)."""
+        w = self.sd[n + '.weight'].double()
+        s, t = bn_affine(self.sd, bn, eps)
+        w = w * s.view(-1, 1, 1, 1, 1)
+        Cout, kd, kh, kw, Cin = w.shape
+        packed = w.reshape(Cout, kd * kh * kw, Cin).permute(1, 2, 0).reshape(kd * kh * kw * Cin, Cout)
+        pc = PackedConv(self._dev(packed), self._dev(t), Cin, Cout)
+        return pc, (kd, kh, kw)
+
+    def vec(self, n):
+        return self._dev(self.sd[n])
