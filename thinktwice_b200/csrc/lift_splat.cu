@@ -235,11 +235,11 @@ size_t tt_voxel_pooling_workspace_bytes(int, int, int, int) { return 0; }
 int tt_voxel_pooling_forward(int batch_size, int num_points, int num_channels, int num_voxel_x, int num_voxel_y,
                              int num_voxel_z, const int* geom_xyz, const float* input_features,
                              float* output_features, int* pos_memo, void* /*workspace*/, tt_stream_t stream) {
-  TT_REQUIRE(geom_xyz && input_features && output_features, "tt_voxel_pooling_forward", "null argument");
   TT_REQUIRE(batch_size >= 0 && num_points >= 0 && num_channels > 0, "tt_voxel_pooling_forward", "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   const long long tp = (long long)batch_size * num_points;
-  if (tp == 0) return TT_OK;
+  if (tp == 0) return TT_OK;                                   // empty input: nothing to add (pointers may be NULL)
+  TT_REQUIRE(geom_xyz && input_features && output_features, "tt_voxel_pooling_forward", "null argument");
   TT_REQUIRE(tp < (1ll << 31) / 3, "tt_voxel_pooling_forward", "too many points for int32 indexing");
   if (pos_memo) {
     voxel_pool_memo_kernel<<<tt_cdiv(tp, 256), 256, 0, st>>>((int)tp, num_points, num_voxel_x, num_voxel_y, num_voxel_z,

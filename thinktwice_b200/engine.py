@@ -54,6 +54,7 @@ class Engine:
         self.device = torch.device(device)
         self.impl = impl
         self.bufs = {}
+        self.prof = None            # bench.py: list of (name, flops, start_event, end_event) per conv launch
         lib.load()
 
     # ------------------------------------------------------------------ buffers
@@ -105,10 +106,17 @@ class Engine:
         if res2 is not None:
             d.res2_ld, d.res2_coff = res2.ld, 0
         d.impl = self.impl if impl is None else impl
+        if self.prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         lib.check(lib.load().tt_conv2d(
             C.byref(d), _p(x.t, x.coff), _p(pw.w), _p(pw.bias),
             _p(res.t, res.coff) if res is not None else None, _p(res2.t, res2.coff) if res2 is not None else None,
             None, None, _p(out.t, out.coff), _stream()), f'tt_conv2d[{name}]')
+        if self.prof is not None:
+            ev1.record()
+            flops = 2.0 * d.N * OH * OW * (pw.KH * pw.KW * pw.Cin // pw.groups) * pw.Cout
+            self.prof.append((name, flops, ev0, ev1))
         return out
 
     def linear(self, x, pw, out=None, name=None, act=0, res=None):

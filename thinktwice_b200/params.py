@@ -210,10 +210,8 @@ def param_spec(model_cfg):
 
 def _init(t, kind, gen):
     with torch.no_grad():
-        if kind in ('conv', 'linear'):                         # xavier_normal_ (code/utils.py:59-80)
-            rf = t[0][0].numel() if t.dim() > 2 else 1
-            std = math.sqrt(2.0 / ((t.shape[0] + t.shape[1]) * rf))
-            t.copy_(torch.randn(t.shape, generator=gen) * std)
+        if kind in ('conv', 'linear'):                         # He-normal: keeps activations O(1) through ReLU stacks
+            t.copy_(torch.randn(t.shape, generator=gen) * math.sqrt(2.0 / t[0].numel()))
         elif kind == 'convT':
             t.copy_(torch.randn(t.shape, generator=gen) * math.sqrt(1.0 / t.shape[0]))
         elif kind == 'spconv':
