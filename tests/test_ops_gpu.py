@@ -250,8 +250,8 @@ def test_lift_splat_matches_oracle_lift_and_pool(eng, B):
     d.X, d.Y, d.Z, d.bev_ld, d.bev_coff, d.anti_transpose = 21, 21, 1, Cc, 0, 0
     ws = torch.empty(lib.load().tt_lift_splat_workspace_bytes(C.byref(d)), dtype=torch.uint8, device='cuda')
     bev = torch.full((B, 21, 21, Cc), 3.0, device='cuda')
-    lib.call('tt_lift_splat', C.byref(d), _p(fd.t), _p(fc.t), _p(mm), _p(m.frustum_u.cuda()), _p(m.frustum_v.cuda()),
-             _p(m.frustum_d.cuda()), _p(bev), _p(ws))
+    fu, fv, fdd = m.frustum_u.cuda(), m.frustum_v.cuda(), m.frustum_d.cuda()      # keep alive across the call
+    lib.call('tt_lift_splat', C.byref(d), _p(fd.t), _p(fc.t), _p(mm), _p(fu), _p(fv), _p(fdd), _p(bev), _p(ws))
     err = relerr(bev.permute(0, 3, 1, 2), ref)
     print('lift_splat err', err)
     assert err < 1e-3                                             # a few boundary points may switch cell (fp32 geometry)
