@@ -86,11 +86,14 @@ int tt_lift_splat(const tt_lift_splat_desc* d, const float* depth_logits, const 
  *   A[m][k], k = tap * Cin_g + c : the input pixel of output row m under tap (kh, kw), channel
  *   g*Cin_g + c, zero outside the image; or, when gather != NULL, row gather[m*taps + tap] of x
  *   (-1 = zero row) — the sparse-conv rulebook.
- *   w: packed [taps * Cin_g][Cout] fp32 (BatchNorm already folded in), bias [Cout] or NULL.
+ *   w: impl 0/1: packed [taps * Cin_g][Cout] fp32 (BatchNorm already folded in); impl 2/3 (tcgen05): packed
+ *      [2][Cout][taps][Cin] = TF32-exact `hi` plane followed by the `lo = w - hi` plane.  bias [Cout] or NULL.
  * Output row m = (n, oh, ow) is stored at pixel (n, oh*oy_mul + oy_add, ow*ox_mul + ox_add) of a
  * [N][yH][yW][y_ld] buffer (a k2s2 transposed conv is four such calls).
  * If m_count != NULL only the first *m_count rows (a device int) are computed.
- * `impl`: 0 = auto, 1 = SIMT fp32 (exact), 2 = tcgen05 TF32x1, 3 = tcgen05 3xTF32 (fp32-class).
+ * `impl`: 0/1 = SIMT fp32 FFMA (exact), 2 = tcgen05 single-pass TF32 (operands rounded to nearest TF32),
+ *         3 = tcgen05 3xTF32 (hi*hi + hi*lo + lo*hi, fp32-class).  impl 2/3 need stride 1, groups 1, channels % 4 == 0
+ *         and `workspace` of tt_conv2d_workspace_bytes(d) bytes (TF32 split planes of the input); else TT_ERR_UNSUPPORTED.
  */
 typedef struct {
   int N, H, W, Cin, x_ld, x_coff;
@@ -106,8 +109,9 @@ typedef struct {
   int M;                          /* gather mode: row capacity; else ignored (N*OH*OW) */
   int impl;
 } tt_conv_desc;
+size_t tt_conv2d_workspace_bytes(const tt_conv_desc* d);
 int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
-              const float* res2, const int* gather, const int* m_count, float* y, tt_stream_t stream);
+              const float* res2, const int* gather, const int* m_count, float* y, void* workspace, tt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (3) memory-bound helpers (torch elementwise / pooling / interpolation ops)

@@ -1,9 +1,413 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM convolution — placeholder until the TMA/TMEM kernel lands.
+// tcgen05 (5th-generation tensor core) implicit-GEMM convolution for sm_100a.
+//
+// GEMM view: M = output pixels (one 128-row tile = a TH x TW rectangle of one image, or 128 consecutive
+// pixels for 1x1 convs), N = Cout (BN-wide tile), K = taps x Cin walked in 32-float (128-byte) slabs.
+//   * operands are staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 3-stage shared-memory ring:
+//     the activation slab of tap (kh, kw) is ONE 4-D box load at a shifted origin — out-of-image pixels and
+//     channels are zero-filled by the TMA unit, so padding / dilation cost nothing;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x BN x K8) with the fp32
+//     accumulator tile living in TMEM (BN columns x 128 lanes);
+//   * precision: fp32 operands are split x = hi + lo with hi, lo both TF32-representable, and every K slab
+//     issues hi*hi + hi*lo + lo*hi ("3xTF32"): ~21 mantissa bits per operand, fp32-class results.
+//     impl == TF32x1 issues hi*hi only (operands rounded to nearest TF32);
+//   * epilogue: 4 warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per instruction), fuse
+//     bias + residual(s) + activation and store 128-bit channels-last rows (concat offset / pixel scatter
+//     for transposed convs handled in the store address).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <cuda.h>
+
 #include "common.cuh"
 
-bool tt_conv2d_tc_supported(const tt_conv_desc*, const void*, const void*, const void*) { return false; }
-int tt_conv2d_tc(const tt_conv_desc*, const float*, const float*, const float*, const float*, const float*, float*,
-                 cudaStream_t) {
-  tt_set_error("tt_conv2d: tcgen05 path not built");
-  return TT_ERR_UNSUPPORTED;
+extern long long g_tt_launches;
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int KS = 32;           // floats per K slab (one 128-byte swizzle row)
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 192;
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+TT_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+TT_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+TT_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+TT_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+TT_DEVICE void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+TT_DEVICE void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+TT_DEVICE void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+TT_DEVICE void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+TT_DEVICE void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 (8 rows x 128 B)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
+TT_DEVICE uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10,
+// a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+TT_DEVICE void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+TT_DEVICE void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct TcArgs {
+  tt_conv_desc d;
+  const float* bias;
+  const float* res;
+  const float* res2;
+  float* y;
+  int TH, TW;            // tile rectangle (TH * TW <= 128); flat mode: TH = 1, TW = 128 over N*H*W pixels
+  int tiles_w, tiles_h;  // tiles per image along W and H
+  int flat;              // 1: 1x1 conv on the flattened pixel axis
+  int n_slabs;           // ceil(Cin / 32)
+  int terms;             // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi only
+  int total_pix;         // N * OH * OW
+};
+
+// operand split: hi = x with the 13 low mantissa bits cleared (exactly TF32), lo = x - hi (exact in fp32).
+// rn != 0 (single-pass TF32 mode): hi = round-to-nearest-even TF32 so the truncation bias disappears.
+__global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long long x_nstride, int HW, int C4,
+                                  float4* __restrict__ hi, float4* __restrict__ lo, long long total, int rn) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    const long long pix = i / C4;
+    const long long n = pix / HW, p = pix % HW;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + n * x_nstride + p * x_ld) + c4);
+    float e[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t u = __float_as_uint(e[j]);
+      if (rn) u += 0xFFFu + ((u >> 13) & 1u);
+      h[j] = __uint_as_float(u & 0xFFFFE000u);
+      l[j] = e[j] - h[j];
+    }
+    hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+    if (lo) lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_BYTES = BM * KS * 4;                    // 16 KB
+  constexpr int B_BYTES = BN * KS * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                                  // [STAGES]
+  uint64_t* empty = bars + STAGES;                        // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;                 // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const tt_conv_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int img, oh0, ow0;
+  long long pix0 = 0;
+  if (p.flat) {
+    img = 0; oh0 = 0; ow0 = 0;
+    pix0 = (long long)blockIdx.x * BM;
+  } else {
+    const int tw = blockIdx.x % p.tiles_w;
+    const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
+    img = blockIdx.x / (p.tiles_w * p.tiles_h);
+    oh0 = th * p.TH;
+    ow0 = tw * p.TW;
+  }
+  const int n0 = blockIdx.y * BN;
+  const int taps = d.KH * d.KW;
+  const int k_iters = taps * p.n_slabs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                        // TMEM allocation: BN fp32 columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KS * 4;   // bytes one activation box delivers
+      const uint32_t tx = (p.terms == 3 ? 2 : 1) * (a_box + B_BYTES);
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        const int tap = it / p.n_slabs, slab = it - tap * p.n_slabs;
+        const int kh = tap / d.KW, kw = tap - kh * d.KW;
+        mbar_expect_tx(&full[s], tx);
+        int cw, ch, cn;
+        if (p.flat) { cw = (int)pix0; ch = 0; cn = 0; }
+        else { cw = ow0 - d.pad + kw * d.dil; ch = oh0 - d.pad + kh * d.dil; cn = img; }
+        tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
+        tma_load_3d(st + 2 * A_BYTES, &map_b_hi, &full[s], slab * KS, tap, n0);
+        if (p.terms == 3) {
+          tma_load_4d(st + A_BYTES, &map_a_lo, &full[s], slab * KS, cw, ch, cn);
+          tma_load_3d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, &full[s], slab * KS, tap, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KS / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+          const uint32_t off = kk * 32;
+          if (p.terms == 3) {
+            umma_tf32(tmem_base, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, (it | kk) != 0);
+            umma_tf32(tmem_base, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
+            umma_tf32(tmem_base, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, 1);
+          } else {
+            umma_tf32(tmem_base, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, (it | kk) != 0);
+          }
+        }
+        tcgen05_commit(&empty[s]);                         // frees the smem slot once these MMAs retire
+      }
+      tcgen05_commit(acc_full);                            // accumulator complete
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5 -> TMEM lane quarters)
+    const int q = warp & 3;                                // this warp may touch TMEM lanes [32q, 32q + 32)
+    const int r = q * 32 + lane;                           // accumulator row = pixel within the tile
+    mbar_wait(acc_full, 0);
+    tcgen05_fence_after();
+    bool valid;
+    long long yoff, rrow, r1pix = 0;
+    if (p.flat) {
+      const long long pix = pix0 + r;
+      valid = pix < p.total_pix;
+      const int HWo = d.OH * d.OW;
+      const long long n = pix / HWo;
+      const int rem = (int)(pix - n * HWo);
+      const int oh = rem / d.OW, ow = rem - oh * d.OW;
+      const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+      yoff = n * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
+      rrow = pix;
+      if (d.res_mode == TT_RES_UP2_NEAREST) r1pix = (n * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW;
+    } else {
+      const int th = r / p.TW, tw = r - th * p.TW;
+      const int oh = oh0 + th, ow = ow0 + tw;
+      valid = (r < p.TH * p.TW) && oh < d.OH && ow < d.OW;
+      const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+      yoff = img * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
+      rrow = ((long long)img * d.OH + oh) * d.OW + ow;
+      if (d.res_mode == TT_RES_UP2_NEAREST) r1pix = ((long long)img * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW;
+    }
+    if (d.res_mode != TT_RES_UP2_NEAREST) r1pix = rrow;
+    float* yrow = p.y + yoff + d.y_coff;
+    const float* r1 = p.res ? p.res + r1pix * d.res_ld + d.res_coff : nullptr;
+    const float* r2 = p.res2 ? p.res2 + rrow * d.res2_ld + d.res2_coff : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= d.Cout) break;                        // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      if (!valid) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = n0 + c0 + j;
+        if (col >= d.Cout) break;
+        float o[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
+        if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+        if (r1) { const float4 t = *reinterpret_cast<const float4*>(r1 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+        if (r2) { const float4 t = *reinterpret_cast<const float4*>(r2 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+        *reinterpret_cast<float4*>(yrow + col) =
+            make_float4(tt_act(o[0], d.act), tt_act(o[1], d.act), tt_act(o[2], d.act), tt_act(o[3], d.act));
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    const char* s = nullptr;
+    cuGetErrorString(r, &s);
+    tt_set_error("tt_conv2d(tc): cuTensorMapEncodeTiled failed: %s", s ? s : "?");
+    return false;
+  }
+  return true;
+}
+
+inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+bool tt_conv2d_tc_supported(const tt_conv_desc* d, const void* x, const void* w, const void* y) {
+  if (d->groups != 1 || d->stride != 1) return false;
+  if (d->Cin % 4 || d->Cout % 4 || d->x_ld % 4 || d->y_ld % 4 || d->x_nstride % 4 || d->y_nstride % 4) return false;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return false;
+  if (d->res_mode != TT_RES_NONE && (d->res_ld % 4)) return false;
+  if (d->res2_ld % 4) return false;
+  if (d->OH != (d->H + 2 * d->pad - d->dil * (d->KH - 1)) || d->OW != (d->W + 2 * d->pad - d->dil * (d->KW - 1))) return false;
+  return true;
+}
+
+extern "C" size_t tt_conv2d_workspace_bytes(const tt_conv_desc* d) {
+  if (!d || d->impl < 2) return 0;
+  const size_t plane = al256((size_t)d->N * d->H * d->W * d->Cin * 4);
+  return (d->impl == 3 ? 2 : 1) * plane;
+}
+
+// w_tc: [2][Cout][taps][Cin] fp32 = explicit hi plane then lo plane (prepared once per layer by the host).
+int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const float* bias, const float* res,
+                 const float* res2, float* y, void* workspace, cudaStream_t st) {
+  const int terms = d->impl == 3 ? 3 : 1;
+  const int taps = d->KH * d->KW;
+  const long long npix_in = (long long)d->N * d->H * d->W;
+  const size_t plane = al256((size_t)npix_in * d->Cin * 4);
+  float* a_hi = static_cast<float*>(workspace);
+  float* a_lo = terms == 3 ? reinterpret_cast<float*>(static_cast<char*>(workspace) + plane) : nullptr;
+  {
+    const long long total = npix_in * (d->Cin / 4);
+    const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * d->W * d->x_ld;
+    const long long nb = (total + 255) / 256;
+    split_tf32_kernel<<<(int)(nb > 148 * 16 ? 148 * 16 : nb), 256, 0, st>>>(x + d->x_coff, d->x_ld, xns, d->H * d->W, d->Cin / 4,
+                                                                         reinterpret_cast<float4*>(a_hi), reinterpret_cast<float4*>(a_lo),
+                                                                         total, terms == 1);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_conv2d(tc split)");
+  }
+  TcArgs a;
+  a.d = *d;
+  a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
+  a.terms = terms;
+  a.n_slabs = (d->Cin + KS - 1) / KS;
+  a.total_pix = d->N * d->OH * d->OW;
+  a.flat = (taps == 1 && d->pad == 0) ? 1 : 0;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int grid_x;
+  if (a.flat) {
+    a.TH = 1; a.TW = BM; a.tiles_w = a.tiles_h = 1;
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)npix_in, 1, 1};
+    cuuint64_t str[3] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)npix_in * d->Cin * 4, (cuuint64_t)npix_in * d->Cin * 4};
+    cuuint32_t box[4] = {KS, BM, 1, 1};
+    if (!encode_map(&ma_hi, a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
+    if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
+    grid_x = tt_cdiv(npix_in, BM);
+  } else {
+    // rectangle with TH * TW <= 128 that wastes the fewest rows
+    int best_th = 1, best_tw = 1;
+    double best = -1;
+    for (int tw = 1; tw <= 128 && tw <= 256; ++tw) {
+      const int th = 128 / tw;
+      if (th < 1) break;
+      const double cover = (double)d->OW * d->OH / ((double)tt_cdiv(d->OW, tw) * tw * tt_cdiv(d->OH, th) * th);
+      const double eff = cover * (tw * th) / 128.0;
+      if (eff > best + 1e-9) { best = eff; best_th = th; best_tw = tw; }
+    }
+    a.TH = best_th; a.TW = best_tw;
+    a.tiles_w = tt_cdiv(d->OW, a.TW); a.tiles_h = tt_cdiv(d->OH, a.TH);
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t str[3] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)d->W * d->Cin * 4, (cuuint64_t)d->H * d->W * d->Cin * 4};
+    cuuint32_t box[4] = {KS, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
+    if (!encode_map(&ma_hi, a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
+    if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
+    grid_x = a.tiles_w * a.tiles_h * d->N;
+  }
+  const int BN = d->Cout > 64 ? 128 : 64;
+  {
+    const size_t wplane = (size_t)d->Cout * taps * d->Cin;
+    cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)taps, (cuuint64_t)d->Cout};
+    cuuint64_t str[2] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)taps * d->Cin * 4};
+    cuuint32_t box[3] = {KS, 1, (cuuint32_t)BN};
+    if (!encode_map(&mb_hi, w_tc, 3, dims, str, box)) return TT_ERR_CUDA;
+    if (!encode_map(&mb_lo, w_tc + wplane, 3, dims, str, box)) return TT_ERR_CUDA;
+  }
+  dim3 grid(grid_x, tt_cdiv(d->Cout, BN));
+  if (BN == 128) {
+    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + 256;
+    static bool set128 = false;
+    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
+    conv_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+  } else {
+    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + 256;
+    static bool set64 = false;
+    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
+    conv_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+  }
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_conv2d(tc)");
+  return TT_OK;
 }

@@ -75,7 +75,7 @@ class EncoderDecoder(nn.Module):
         dev = torch.device(device)
         lib.require_cuda(dev)
         self.eng = e = Engine(dev, impl)
-        pk = Packer(self.params.state_dict(), dev)
+        pk = Packer(self.params.state_dict(), dev, tc_mode=impl if impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) else 0)
         self.img_encoder.prepare(pk, e)
         self.lidar_encoder.prepare(pk, e)
         self.decoder.prepare(pk, e, self)

@@ -43,10 +43,11 @@ class FMap:
 
 class PackedConv:
     """weights of one conv / linear in kernel layout: w [taps*Cin_g][Cout] (BatchNorm folded), bias [Cout]|None."""
-    __slots__ = ('w', 'bias', 'Cin', 'Cout', 'KH', 'KW', 'groups')
+    __slots__ = ('w', 'bias', 'Cin', 'Cout', 'KH', 'KW', 'groups', 'w_tc')
 
-    def __init__(self, w, bias, Cin, Cout, KH=1, KW=1, groups=1):
+    def __init__(self, w, bias, Cin, Cout, KH=1, KW=1, groups=1, w_tc=None):
         self.w, self.bias, self.Cin, self.Cout, self.KH, self.KW, self.groups = w, bias, Cin, Cout, KH, KW, groups
+        self.w_tc = w_tc            # [2][Cout][taps][Cin] TF32 hi / lo planes for the tcgen05 path (or None)
 
 
 class Engine:
@@ -54,6 +55,8 @@ class Engine:
         self.device = torch.device(device)
         self.impl = impl
         self.bufs = {}
+        self.tc_ws = None           # grow-only workspace of the tcgen05 path (TF32 split planes)
+        self.tc_min_rows = 512
         self.prof = None            # bench.py: list of (name, flops, start_event, end_event) per conv launch
         lib.load()
 
@@ -105,14 +108,27 @@ class Engine:
             assert res.C == pw.Cout
         if res2 is not None:
             d.res2_ld, d.res2_coff = res2.ld, 0
-        d.impl = self.impl if impl is None else impl
+        impl = self.impl if impl is None else impl
+        # tcgen05 path: dense stride-1 convs with enough work to fill 128-row tiles; everything else stays SIMT fp32
+        use_tc = (impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and stride == 1 and pw.groups == 1
+                  and x.ld % 4 == 0 and x.coff % 4 == 0 and out.ld % 4 == 0 and out.coff % 4 == 0
+                  and (res is None or (res.ld % 4 == 0 and res.coff % 4 == 0)) and (res2 is None or (res2.ld % 4 == 0 and res2.coff % 4 == 0))
+                  and x_nstride % 4 == 0 and y_nstride % 4 == 0
+                  and d.N * OH * OW >= self.tc_min_rows and pw.Cout >= 32)
+        d.impl = impl if use_tc else lib.IMPL_SIMT
+        ws = None
+        if use_tc:
+            need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))
+            if self.tc_ws is None or self.tc_ws.numel() < need:
+                self.tc_ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+            ws = self.tc_ws
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         lib.check(lib.load().tt_conv2d(
-            C.byref(d), _p(x.t, x.coff), _p(pw.w), _p(pw.bias),
+            C.byref(d), _p(x.t, x.coff), _p(pw.w_tc if use_tc else pw.w), _p(pw.bias),
             _p(res.t, res.coff) if res is not None else None, _p(res2.t, res2.coff) if res2 is not None else None,
-            None, None, _p(out.t, out.coff), _stream()), f'tt_conv2d[{name}]')
+            None, None, _p(out.t, out.coff), _p(ws), _stream()), f'tt_conv2d[{name}]')
         if self.prof is not None:
             ev1.record()
             flops = 2.0 * d.N * OH * OW * (pw.KH * pw.KW * pw.Cin // pw.groups) * pw.Cout
@@ -141,7 +157,7 @@ class Engine:
         d.taps, d.M = taps, cap
         d.impl = lib.IMPL_SIMT
         lib.check(lib.load().tt_conv2d(C.byref(d), _p(feats), _p(pw.w), _p(pw.bias), _p(res), None, _p(nbr), _p(count),
-                                       _p(out), _stream()), f'tt_conv2d[sparse {name}]')
+                                       _p(out), None, _stream()), f'tt_conv2d[sparse {name}]')
         return out
 
     # ------------------------------------------------------------------ memory-bound ops

@@ -75,7 +75,7 @@ def load():
     lib.tt_last_error.restype = C.c_char_p
     lib.tt_launch_count.restype = C.c_longlong
     for n in ('tt_voxel_pooling_workspace_bytes', 'tt_lift_splat_workspace_bytes', 'tt_voxelize_workspace_bytes',
-              'tt_rulebook_workspace_bytes'):
+              'tt_rulebook_workspace_bytes', 'tt_conv2d_workspace_bytes'):
         getattr(lib, n).restype = C.c_size_t
     _lib = lib
     return lib
@@ -83,7 +83,7 @@ def load():
 
 EXPORTS = [
     'tt_version', 'tt_last_error', 'tt_launch_count', 'tt_voxel_pooling_workspace_bytes', 'tt_voxel_pooling_forward',
-    'tt_lift_splat_workspace_bytes', 'tt_lift_splat', 'tt_conv2d', 'tt_nchw_to_nhwc', 'tt_nhwc_to_nchw',
+    'tt_lift_splat_workspace_bytes', 'tt_lift_splat', 'tt_conv2d', 'tt_conv2d_workspace_bytes', 'tt_nchw_to_nhwc', 'tt_nhwc_to_nchw',
     'tt_maxpool3x3s2', 'tt_upsample2x_bilinear_ac', 'tt_global_avgpool', 'tt_broadcast_rows', 'tt_se_gate', 'tt_se_pool',
     'tt_se_apply', 'tt_anti_transpose', 'tt_copy2d', 'tt_layernorm', 'tt_eltwise', 'tt_fill', 'tt_dcn_im2col',
     'tt_voxelize_workspace_bytes', 'tt_voxelize_mean', 'tt_rulebook_workspace_bytes', 'tt_sparse_rulebook',
@@ -134,10 +134,5 @@ def i4(v):
 # ---------------------------------------------------------------------------------------------
 # thin typed wrappers (pointer arithmetic for channel offsets is done by the callers through `_p`)
 # ---------------------------------------------------------------------------------------------
-def conv2d(desc, x, w, bias, y, res=None, res2=None, gather=None, m_count=None, x_off=0, y_off=0, res_off=0):
-    check(load().tt_conv2d(C.byref(desc), _p(x, x_off), _p(w), _p(bias), _p(res, res_off), _p(res2), _p(gather),
-                           _p(m_count), _p(y, y_off), _stream()), 'tt_conv2d')
-
-
 def call(name, *args):
     check(getattr(load(), name)(*args, _stream()), name)

@@ -15,10 +15,30 @@ def bn_affine(sd, n, eps):
     return s, t
 
 
+def tf32_split(w, rn=False):
+    """w (fp32) -> (hi, lo): hi is exactly TF32 (13 low mantissa bits clear), lo = w - hi (exact).
+    rn=True rounds hi to nearest-even TF32 instead of truncating (single-pass TF32 mode)."""
+    w = w.float().contiguous()
+    u = w.view(torch.int32)
+    if rn:
+        u = u + 0xFFF + ((u >> 13) & 1)
+    hi = (u & ~0x1FFF).view(torch.float32)
+    return hi, w - hi
+
+
 class Packer:
-    def __init__(self, sd, device):
+    def __init__(self, sd, device, tc_mode=0):
         self.sd = {k: v.detach().cpu() for k, v in sd.items()}
         self.device = device
+        self.tc_mode = tc_mode      # 0: SIMT only; 2 / 3: also pack [2][Cout][taps][Cin] TF32 hi/lo planes for tcgen05
+
+    def _tc(self, w_ohwi):
+        """w_ohwi: (Cout, taps, Cin) float64 -> device tensor [2][Cout][taps][Cin] or None."""
+        Cout, taps, Cin = w_ohwi.shape
+        if self.tc_mode not in (2, 3) or Cin % 4 or Cout % 4 or Cout < 32:
+            return None
+        hi, lo = tf32_split(w_ohwi.float(), rn=(self.tc_mode == 2))
+        return torch.stack([hi, lo]).contiguous().to(self.device)
 
     def _dev(self, t):
         return None if t is None else t.float().contiguous().to(self.device)
@@ -49,7 +69,8 @@ class Packer:
             w = torch.cat([w, w.new_zeros(Cout, cin_pad - Cg, KH, KW)], 1)
             Cg = cin_pad
         packed = w.permute(2, 3, 1, 0).reshape(KH * KW * Cg, Cout)
-        return PackedConv(self._dev(packed), self._dev(b), Cg * groups, Cout, KH, KW, groups)
+        w_tc = self._tc(w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cg)) if groups == 1 else None
+        return PackedConv(self._dev(packed), self._dev(b), Cg * groups, Cout, KH, KW, groups, w_tc)
 
     def linear(self, n, bn_after=None, eps=1e-5, in_affine=None, cin_pad=None, weight=None, bias=None, cin_index=None):
         """Linear (Cout, Cin).  in_affine=(s, t): the input is s*x + t (a folded BatchNorm1d in front);
@@ -71,7 +92,7 @@ class Packer:
         if cin_pad is not None and cin_pad > Cin:
             w = torch.cat([w, w.new_zeros(Cout, cin_pad - Cin)], 1)
             Cin = cin_pad
-        return PackedConv(self._dev(w.t()), self._dev(b), Cin, Cout)
+        return PackedConv(self._dev(w.t()), self._dev(b), Cin, Cout, w_tc=self._tc(w.reshape(Cout, 1, Cin)))
 
     def conv1x1_as_linear(self, n, **kw):
         w = self.sd[n + '.weight']
@@ -88,7 +109,8 @@ class Packer:
             b = t if b is None else b * s + t
         Cin, Cout = w.shape[:2]
         bd = self._dev(b)
-        return [[PackedConv(self._dev(w[:, :, i, j]), bd, Cin, Cout) for j in range(2)] for i in range(2)]
+        return [[PackedConv(self._dev(w[:, :, i, j]), bd, Cin, Cout, w_tc=self._tc(w[:, :, i, j].t().reshape(Cout, 1, Cin)))
+                 for j in range(2)] for i in range(2)]
 
     def spconv(self, n, bn, eps=1e-3):
         """spconv weight (Cout, kd, kh, kw, Cin) + BatchNorm1d -> PackedConv with K = (tap, cin)."""
