@@ -123,6 +123,10 @@ def main():
     ap.add_argument('--batch', type=int, default=1, help='frames per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-worker'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
+    ap.add_argument('--dump-convs', default=None, help='write per-conv-launch (name, flops, ms) of one step to this JSON file')
+    ap.add_argument('--conv', default='3xtf32', choices=['simt', '3xtf32', 'tf32'],
+                    help='dense-conv engine: tcgen05 3xTF32 (fp32-class, default), tcgen05 single-pass TF32, or SIMT fp32')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -134,7 +138,7 @@ def main():
     cfg = Config.fromfile(DEFAULT_CONFIG)
     base = {'metric': METRIC, 'unit': 'frames/s', 'n_gpus': args.gpus, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'data': 'synthetic (seeded N(0,1) images, synthetic LiDAR, random-init weights)',
-            'config': {'workload': WORKLOAD, 'frames_per_gpu_per_step': args.batch, 'refine_num': 5,
+            'config': {'workload': WORKLOAD, 'frames_per_gpu_per_step': args.batch, 'refine_num': 5, 'conv_engine': args.conv, 'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set (0.5 GB weights + >1 GB activations) exceeds the 126 MB L2; no explicit flush'}}
 
     if args.impl == 'reference':
@@ -161,7 +165,7 @@ def main():
     from thinktwice_b200.synthetic import make_batch
 
     model = build_model(cfg.model)
-    model.prepare(dev)
+    model.prepare(dev, impl={'simt': lib.IMPL_SIMT, '3xtf32': lib.IMPL_3XTF32, 'tf32': lib.IMPL_TF32}[args.conv])
     B = args.batch
     host = make_batch(cfg, B, seed=100 + rank)                    # every rank owns different frames (weak scaling)
     for k in ('img', 'points', 'speed', 'target_point', 'target_command'):
@@ -194,25 +198,33 @@ def main():
             dist.barrier()
         return float(ms.item())
 
+    n_eager = lib.launch_count()
+    step(resident)                                               # eager step: allocates every buffer, counts launches
+    torch.cuda.synchronize()
+    launches_per_step = lib.launch_count() - n_eager
+    if not args.no_graph:
+        model.enable_cuda_graph()                                # the device half becomes one CUDA graph (captured on next call)
     for _ in range(max(args.warmup, 3)):
         step(resident)
     torch.cuda.synchronize()
     stop, samples = threading.Event(), []
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
     th.start()
-    n0 = lib.launch_count()
     ms = timed(resident, args.steps, read_back=False)
-    launches = lib.launch_count() - n0
+    launches = launches_per_step * args.steps                    # graph replays execute the same kernel nodes every step
     ms_e2e = timed(host, args.steps, read_back=True)
     stop.set(); th.join(timeout=2)
 
     # ---- roofline of the dominant kernel family (implicit-GEMM conv): per-launch CUDA events on the launching stream
+    model.use_graph = False                                      # per-launch events need eager launches
     model.eng.prof = []
     step(resident)
     torch.cuda.synchronize()
     conv_ms = sum(a.elapsed_time(b) for (_, _, a, b) in model.eng.prof)
     conv_flops = sum(f for (_, f, _, _) in model.eng.prof)
     n_conv = len(model.eng.prof)
+    if args.dump_convs and rank == 0:
+        json.dump([(n, f, a.elapsed_time(b)) for (n, f, a, b) in model.eng.prof], open(args.dump_convs, 'w'))
     model.eng.prof = None
     tensor_peak, hbm_peak, peak_src = load_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -224,7 +236,7 @@ def main():
     frames = args.steps * B * world
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     line = dict(base, value=frames / (ms * 1e-3), steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
-                dtype='f32', gpu_launches=launches, clocks=summarize_clocks(samples),
+                dtype={'simt': 'f32', '3xtf32': 'f32 (3xTF32 tensor-core products, fp32 accumulate)', 'tf32': 'tf32'}[args.conv], gpu_launches=launches, clocks=summarize_clocks(samples),
                 e2e={'value': frames / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                      'd2h_bytes_per_step': B * 6 * 4 * 2 * 4},
                 roofline={'bound': 'tensor', 'kernel': 'conv_igemm (implicit-GEMM conv / linear family)',

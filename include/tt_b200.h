@@ -94,6 +94,8 @@ int tt_lift_splat(const tt_lift_splat_desc* d, const float* depth_logits, const 
  * `impl`: 0/1 = SIMT fp32 FFMA (exact), 2 = tcgen05 single-pass TF32 (operands rounded to nearest TF32),
  *         3 = tcgen05 3xTF32 (hi*hi + hi*lo + lo*hi, fp32-class).  impl 2/3 need stride 1, groups 1, channels % 4 == 0
  *         and `workspace` of tt_conv2d_workspace_bytes(d) bytes (TF32 split planes of the input); else TT_ERR_UNSUPPORTED.
+ *         For impl 0/1 the workspace is optional: when given (size from tt_conv2d_workspace_bytes) small-M / large-K
+ *         layers run split-K with a deterministic fixed-order reduction.
  */
 typedef struct {
   int N, H, W, Cin, x_ld, x_coff;
@@ -102,6 +104,7 @@ typedef struct {
   int OH, OW;
   int y_ld, y_coff, yH, yW, oy_mul, oy_add, ox_mul, ox_add;
   int act;
+  int bias_n_mod;                 /* 0: bias[Cout]; k > 0: per-image bias table, row (n % k) of bias[k][Cout] */
   int res_mode, res_ld, res_coff; /* res: same pixel grid as the output rows (SAME) or coarser (UP2_NEAREST) */
   int res_H, res_W;               /* UP2_NEAREST: residual map size; source pixel = floor(o * res / O) */
   int res2_ld, res2_coff;         /* optional second SAME residual */

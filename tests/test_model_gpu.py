@@ -15,7 +15,7 @@ def relerr(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
-def build_pair(cfg_path, B, num_points, seed=0, calib_B=None):
+def build_pair(cfg_path, B, num_points, seed=0, impl=1):
     from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
     from thinktwice_b200.config import Config
     from thinktwice_b200.registry import build_model
@@ -27,7 +27,7 @@ def build_pair(cfg_path, B, num_points, seed=0, calib_B=None):
     calibrate_bn(oracle, batch)
     model = build_model(cfg.model)
     model.load_state_dict(oracle.state_dict())
-    model.prepare('cuda:0')
+    model.prepare('cuda:0', impl=impl)
     return cfg, oracle, model, batch
 
 
@@ -55,9 +55,11 @@ def compare_all(oracle, model, batch, tol=TOL):
     return errs
 
 
-def test_plumbing_config_b1_matches_oracle():
+@pytest.mark.parametrize('impl', [1, 3])
+def test_plumbing_config_b1_matches_oracle(impl):
+    """impl 1: every contraction on the SIMT fp32 kernel; impl 3: dense convs on tcgen05 3xTF32."""
     from thinktwice_b200.config import PLUMBING_CONFIG
-    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000)
+    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000, impl=impl)
     compare_all(oracle, model, batch)
 
 
@@ -76,8 +78,25 @@ def test_repeat_forward_is_bitwise_stable_where_deterministic():
     assert float((a - b).abs().max()) < 1e-4 * float(a.abs().max())
 
 
+def test_cuda_graph_replay_equals_eager():
+    from thinktwice_b200.config import PLUMBING_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg, _, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000, impl=3)
+    eager = {k: model.forward_inference(batch)[k].clone() for k in ('pred_wp', 'mu_branches', 'refine_BEV_feature')}
+    model.enable_cuda_graph()
+    for _ in range(2):                                              # capture, then a pure replay
+        pred = model.forward_inference(batch)
+    for k, v in eager.items():
+        assert relerr(pred[k], v) < 1e-5, k
+    other = make_batch(cfg, 1, seed=7, num_points=2000)             # new inputs through the same graph
+    p2 = model.forward_inference(other)['pred_wp'].clone()
+    model.use_graph = False
+    assert relerr(p2, model.forward_inference(other)['pred_wp']) < 1e-5
+
+
 def test_full_thinktwice_config_b1_matches_oracle():
     """BASELINE.json configs[1]: thinktwice.py, 4 cams x 2 sweeps 448x896 + 40k LiDAR points, K=5, batch 1."""
     from thinktwice_b200.config import DEFAULT_CONFIG
-    _, oracle, model, batch = build_pair(DEFAULT_CONFIG, 1, 40000)
+    _, oracle, model, batch = build_pair(DEFAULT_CONFIG, 1, 40000, impl=3)
     compare_all(oracle, model, batch)
+

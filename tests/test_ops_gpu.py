@@ -55,6 +55,8 @@ CONV_CASES = [
     (3, 8, 8, 512, 18, 3, 1, 1, 1, 1, True, 0),         # DCN offset conv: Cout % 4 != 0
     (1, 40, 40, 256, 256, 3, 1, 1, 1, 1, True, 2),      # big tile path, gelu
     (4, 64, 64, 128, 64, 3, 2, 1, 1, 1, True, 1),       # 128x64 tile path
+    (4, 2, 2, 256, 512, 3, 1, 1, 1, 1, True, 1),        # pyramid MLP2: M = 16, K = 2304 -> split-K
+    (1, 21, 21, 2080, 128, 3, 1, 1, 1, 1, True, 1),     # decoder BEV update: M = 441, K = 18720 -> split-K
 ]
 
 
@@ -121,7 +123,7 @@ def test_conv_transpose_k2s2(eng):
 
 def test_linear_small_and_padded(eng):
     gen = torch.Generator().manual_seed(4)
-    for rows, cin, cout in [(1, 384, 512), (5, 1543, 512), (33, 514, 2), (480, 256, 1024)]:
+    for rows, cin, cout in [(1, 384, 512), (5, 1543, 512), (33, 514, 2), (480, 256, 1024), (1, 2304, 512), (4, 1024, 512)]:
         x = torch.randn(rows, cin, generator=gen).cuda()
         w = torch.randn(cout, cin, generator=gen) * cin ** -0.5
         b = torch.randn(cout, generator=gen)

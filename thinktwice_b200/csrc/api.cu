@@ -15,7 +15,7 @@ void tt_set_error(const char* fmt, ...) {
 }
 
 int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
-                   const float* res2, const int* gather, const int* m_count, float* y, cudaStream_t st);
+                   const float* res2, const int* gather, const int* m_count, float* y, void* workspace, cudaStream_t st);
 int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
                  const float* res2, float* y, void* workspace, cudaStream_t st);
 bool tt_conv2d_tc_supported(const tt_conv_desc* d, const void* x, const void* w, const void* y);
@@ -43,7 +43,7 @@ int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float
     TT_REQUIRE(workspace != nullptr, "tt_conv2d", "tcgen05 path needs tt_conv2d_workspace_bytes() of workspace");
     return tt_conv2d_tc(d, x, w, bias, res, res2, y, workspace, st);
   }
-  return tt_conv2d_simt(d, x, w, bias, res, res2, gather, m_count, y, st);
+  return tt_conv2d_simt(d, x, w, bias, res, res2, gather, m_count, y, workspace, st);
 }
 
 }  // extern "C"

@@ -24,6 +24,8 @@ struct ConvArgs {
   const int* m_count;
   float* y;
   int M, Cin_g, Cout_g, Kg, taps;
+  int splits, k_per_split;   // split-K (small-M / large-K layers): partial sums go to `partial`, reduced by a 2nd kernel
+  float* partial;            // [splits][M][Cout]
 };
 
 constexpr int BK = 16;
@@ -39,7 +41,10 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
 
   const tt_conv_desc& d = p.d;
   const int tid = threadIdx.x;
-  const int g = blockIdx.z;
+  const int g = blockIdx.z / p.splits;
+  const int sp = blockIdx.z - g * p.splits;
+  const int k_begin = sp * p.k_per_split;
+  const int k_end = min(p.Kg, k_begin + p.k_per_split);
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   int M = p.M;
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       const int kg = k0 + a_k + j;
       if (VECA) {
-        if (a_valid && kg < p.Kg) {
+        if (a_valid && kg < k_end) {
           const int tap = kg / p.Cin_g;
           const int c = kg - tap * p.Cin_g;
           const float* src = nullptr;
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int k = kg + i;
-            if (k < p.Kg) {
+            if (k < k_end) {
               const int tap = k / p.Cin_g;
               const int c = k - tap * p.Cin_g;
               if (p.gather) {
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
       const int k = k0 + b_k + ps * (256 / BTPR);
       const int n = n0 + b_col;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k < p.Kg) {
+      if (k < k_end) {
         const float* src = wg + (long long)k * d.Cout + n;
         if (VECB) {
           if (n < p.Cout_g) v = __ldg(reinterpret_cast<const float4*>(src));
@@ -158,16 +163,16 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  const int nk = (p.Kg + BK - 1) / BK;
-  load_a(0);
-  load_b(0);
+  const int nk = (k_end - k_begin + BK - 1) / BK;
+  load_a(k_begin);
+  load_b(k_begin);
   store_smem(0);
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) {
-      load_a((kt + 1) * BK);
-      load_b((kt + 1) * BK);
+      load_a(k_begin + (kt + 1) * BK);
+      load_b(k_begin + (kt + 1) * BK);
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
@@ -193,6 +198,23 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
     }
   }
 
+  // ---- split-K: raw partial sums, the reduce kernel applies the epilogue
+  if (p.splits > 1) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int row = m0 + (i / 4) * (BM / QM) + ty * 4 + (i % 4);
+      if (row >= M) continue;
+      float* prow = p.partial + ((long long)sp * p.M + row) * d.Cout + g * p.Cout_g;
+#pragma unroll
+      for (int q = 0; q < QN; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = n0 + q * (BN / QN) + tx * 4 + j;
+          if (col < p.Cout_g) prow[col] = acc[i][q * 4 + j];
+        }
+    }
+    return;
+  }
   // ---- epilogue
   const bool vec_out = VECB && (d.y_ld % 4 == 0) && (d.y_coff % 4 == 0) &&
                        (p.res == nullptr || (d.res_ld % 4 == 0 && d.res_coff % 4 == 0)) &&
@@ -202,13 +224,14 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
     const int row = m0 + (i / 4) * (BM / QM) + ty * 4 + (i % 4);
     if (row >= M) continue;
     long long yoff, rpix = row, r1pix = row;
+    int n = 0;
     if (p.gather) {
       yoff = (long long)row * d.y_ld;
     } else {
       const int ow = row % d.OW;
       const int t = row / d.OW;
       const int oh = t % d.OH;
-      const int n = t / d.OH;
+      n = t / d.OH;
       yoff = n * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
       if (d.res_mode == TT_RES_UP2_NEAREST) {
         const int rh = (oh * d.res_H) / d.OH, rw = (ow * d.res_W) / d.OW;
@@ -218,7 +241,7 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
     float* yrow = p.y + yoff + d.y_coff + g * p.Cout_g;
     const float* r1 = p.res ? p.res + r1pix * d.res_ld + d.res_coff + g * p.Cout_g : nullptr;
     const float* r2 = p.res2 ? p.res2 + rpix * d.res2_ld + d.res2_coff + g * p.Cout_g : nullptr;
-    const float* bs = p.bias ? p.bias + g * p.Cout_g : nullptr;
+    const float* bs = p.bias ? p.bias + (d.bias_n_mod ? (long long)(n % d.bias_n_mod) * d.Cout : 0) + g * p.Cout_g : nullptr;
 #pragma unroll
     for (int q = 0; q < QN; ++q) {
       const int col = n0 + q * (BN / QN) + tx * 4;
@@ -248,9 +271,39 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
   }
 }
 
+__global__ void splitk_reduce_kernel(const ConvArgs p) {
+  const tt_conv_desc& d = p.d;
+  int M = p.M;
+  if (p.m_count) M = min(M, *p.m_count);
+  const long long total = (long long)M * d.Cout;
+  const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = i % d.Cout;
+    const int row = i / d.Cout;
+    float v = 0.f;
+    for (int s = 0; s < p.splits; ++s) v += p.partial[((long long)s * p.M + row) * d.Cout + col];   // fixed order
+    long long yoff, r1pix = row;
+    int n = 0;
+    if (p.gather) {
+      yoff = (long long)row * d.y_ld;
+    } else {
+      const int ow = row % d.OW;
+      const int t = row / d.OW;
+      const int oh = t % d.OH;
+      n = t / d.OH;
+      yoff = n * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
+      if (d.res_mode == TT_RES_UP2_NEAREST) r1pix = ((long long)n * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW;
+    }
+    if (p.bias) v += __ldg(p.bias + (d.bias_n_mod ? (long long)(n % d.bias_n_mod) * d.Cout : 0) + col);
+    if (p.res) v += p.res[r1pix * d.res_ld + d.res_coff + col];
+    if (p.res2) v += p.res2[(long long)row * d.res2_ld + d.res2_coff + col];
+    p.y[yoff + d.y_coff + col] = tt_act(v, d.act);
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 void launch_cfg(const ConvArgs& a, bool veca, bool vecb, cudaStream_t st) {
-  dim3 grid(tt_cdiv(a.M, BM), tt_cdiv(a.Cout_g, BN), a.d.groups);
+  dim3 grid(tt_cdiv(a.M, BM), tt_cdiv(a.Cout_g, BN), a.d.groups * a.splits);
   if (veca && vecb) conv_igemm_simt<BM, BN, TM, TN, true, true><<<grid, 256, 0, st>>>(a);
   else if (veca) conv_igemm_simt<BM, BN, TM, TN, true, false><<<grid, 256, 0, st>>>(a);
   else if (vecb) conv_igemm_simt<BM, BN, TM, TN, false, true><<<grid, 256, 0, st>>>(a);
@@ -261,8 +314,21 @@ void launch_cfg(const ConvArgs& a, bool veca, bool vecb, cudaStream_t st) {
 
 extern long long g_tt_launches;
 
+// split-K plan shared by the launcher and tt_conv2d_workspace_bytes
+int tt_simt_splits(const tt_conv_desc* d, int has_gather) {
+  const int taps = has_gather ? d->taps : d->KH * d->KW;
+  const int M = has_gather ? d->M : d->N * d->OH * d->OW;
+  const int Kg = taps * (d->Cin / d->groups);
+  const long long tiles = (long long)tt_cdiv(M, 64) * tt_cdiv(d->Cout / d->groups, 64) * d->groups;
+  if (has_gather || tiles >= 74 || Kg < 1024) return 1;
+  int s = tt_cdiv(296, tiles);
+  if (s > Kg / 256) s = Kg / 256;
+  if (s > 32) s = 32;
+  return s < 2 ? 1 : s;
+}
+
 int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
-                   const float* res2, const int* gather, const int* m_count, float* y, cudaStream_t st) {
+                   const float* res2, const int* gather, const int* m_count, float* y, void* workspace, cudaStream_t st) {
   ConvArgs a;
   a.d = *d;
   a.x = x; a.w = w; a.bias = bias; a.res = res; a.res2 = res2; a.gather = gather; a.m_count = m_count; a.y = y;
@@ -277,6 +343,9 @@ int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const 
   }
   a.Kg = a.taps * a.Cin_g;
   if (a.M <= 0) return TT_OK;
+  a.splits = workspace ? tt_simt_splits(d, gather != nullptr) : 1;
+  a.k_per_split = a.splits > 1 ? tt_cdiv(tt_cdiv(a.Kg, a.splits), BK) * BK : a.Kg;
+  a.partial = static_cast<float*>(workspace);
   const bool veca = (a.Cin_g % 4 == 0) && (d->x_ld % 4 == 0) && (d->x_coff % 4 == 0) && (d->x_nstride % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const bool vecb = (a.Cout_g % 4 == 0) && (d->Cout % 4 == 0) && (d->y_nstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
@@ -286,6 +355,16 @@ int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const 
                     (res2 == nullptr || (reinterpret_cast<uintptr_t>(res2) & 15) == 0);
   // tile choice: big tiles when they still fill the 148 SMs, otherwise smaller ones
   const long long big = (long long)tt_cdiv(a.M, 128) * tt_cdiv(a.Cout_g, 128) * d->groups;
+  if (a.splits > 1) {
+    launch_cfg<64, 64, 4, 4>(a, veca, vecb, st);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_conv2d(simt split-k)");
+    const long long total = (long long)a.M * d->Cout;
+    splitk_reduce_kernel<<<(int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256), 256, 0, st>>>(a);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_conv2d(simt split-k reduce)");
+    return TT_OK;
+  }
   if (a.Cout_g > 64 && big >= 148) launch_cfg<128, 128, 8, 8>(a, veca, vecb, st);
   else if (a.Cout_g <= 64 && (long long)tt_cdiv(a.M, 128) * d->groups >= 148) launch_cfg<128, 64, 8, 4>(a, veca, vecb, st);
   else launch_cfg<64, 64, 4, 4>(a, veca, vecb, st);

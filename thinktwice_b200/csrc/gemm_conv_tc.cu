@@ -7,9 +7,13 @@
 //     channels are zero-filled by the TMA unit, so padding / dilation cost nothing;
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x BN x K8) with the fp32
 //     accumulator tile living in TMEM (BN columns x 128 lanes);
-//   * precision: fp32 operands are split x = hi + lo with hi, lo both TF32-representable, and every K slab
-//     issues hi*hi + hi*lo + lo*hi ("3xTF32"): ~21 mantissa bits per operand, fp32-class results.
-//     impl == TF32x1 issues hi*hi only (operands rounded to nearest TF32);
+//   * precision: fp32 operands are split x = hi + lo with hi, lo both TF32-representable (round-to-nearest), and
+//     every K slab issues hi*hi + hi*lo + lo*hi ("3xTF32": ~21 mantissa bits per operand).  The tensor core adds
+//     into its fp32 accumulator with truncation, an error that grows linearly with the number of accumulations
+//     (measured: ~8e-9 * K relative), so (a) the two small correction products go to their OWN TMEM accumulator and
+//     (b) every CHUNK K-slabs the epilogue warps drain both accumulators with tcgen05.ld and fold them into fp32
+//     registers with round-to-nearest FADDs while the MMA warp already fills the other accumulator pair (TMEM
+//     ping-pong: 2 x (main + corr) x BN columns = all 512 columns at BN = 128).  impl == TF32x1 issues hi*hi only;
 //   * epilogue: 4 warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per instruction), fuse
 //     bias + residual(s) + activation and store 128-bit channels-last rows (concat offset / pixel scatter
 //     for transposed convs handled in the store address).
@@ -112,11 +116,12 @@ struct TcArgs {
   int flat;              // 1: 1x1 conv on the flattened pixel axis
   int n_slabs;           // ceil(Cin / 32)
   int terms;             // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi only
+  int chunk;             // K slabs accumulated inside TMEM before the epilogue folds them into fp32 registers
   int total_pix;         // N * OH * OW
 };
 
-// operand split: hi = x with the 13 low mantissa bits cleared (exactly TF32), lo = x - hi (exact in fp32).
-// rn != 0 (single-pass TF32 mode): hi = round-to-nearest-even TF32 so the truncation bias disappears.
+// operand split: hi = RN_tf32(x), lo = RN_tf32(x - hi); both exactly representable in TF32, so the tensor core's
+// own fp32->tf32 conversion (truncation) is exact and no rounding bias enters the products.
 __global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long long x_nstride, int HW, int C4,
                                   float4* __restrict__ hi, float4* __restrict__ lo, long long total, int rn) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -128,9 +133,11 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long lo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t u = __float_as_uint(e[j]);
-      if (rn) u += 0xFFFu + ((u >> 13) & 1u);
+      u += 0xFFFu + ((u >> 13) & 1u);                        // round-to-nearest-even at TF32 precision
       h[j] = __uint_as_float(u & 0xFFFFE000u);
-      l[j] = e[j] - h[j];
+      uint32_t v = __float_as_uint(e[j] - h[j]);             // exact in fp32
+      v += 0xFFFu + ((v >> 13) & 1u);
+      l[j] = __uint_as_float(v & 0xFFFFE000u);
     }
     hi[i] = make_float4(h[0], h[1], h[2], h[3]);
     if (lo) lo[i] = make_float4(l[0], l[1], l[2], l[3]);
@@ -145,16 +152,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr int A_BYTES = BM * KS * 4;                    // 16 KB
   constexpr int B_BYTES = BN * KS * 4;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int TMEM_COLS = 4 * BN;                       // 2 (ping-pong) x {main, corr} x BN fp32 columns
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                                  // [STAGES]
-  uint64_t* empty = bars + STAGES;                        // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;                 // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* full = bars;                                  // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;                        // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;                 // [2]       MMA -> epilogue (chunk finished)
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;            // [2]       epilogue -> MMA (accumulators drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const tt_conv_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile coordinates
   int img, oh0, ow0;
   long long pix0 = 0;
   if (p.flat) {
@@ -170,14 +178,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int n0 = blockIdx.y * BN;
   const int taps = d.KH * d.KW;
   const int k_iters = taps * p.n_slabs;
+  const int n_chunks = (k_iters + p.chunk - 1) / p.chunk;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(acc_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }   // 4 epilogue warps arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {                                        // TMEM allocation: BN fp32 columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tcgen05_fence_before();
@@ -200,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_expect_tx(&full[s], tx);
         int cw, ch, cn;
         if (p.flat) { cw = (int)pix0; ch = 0; cn = 0; }
-        else { cw = ow0 - d.pad + kw * d.dil; ch = oh0 - d.pad + kh * d.dil; cn = img; }
+        else { cw = ow0 * d.stride - d.pad + kw * d.dil; ch = oh0 * d.stride - d.pad + kh * d.dil; cn = img; }
         tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
         tma_load_3d(st + 2 * A_BYTES, &map_b_hi, &full[s], slab * KS, tap, n0);
         if (p.terms == 3) {
@@ -213,41 +222,76 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      int it = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);        // epilogue has drained this accumulator pair
         tcgen05_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t t_main = tmem_base + (uint32_t)(b * 2 * BN), t_corr = t_main + BN;
+        const int it_end = min(it + p.chunk, k_iters);
+        bool first = true;
+        for (; it < it_end; ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < KS / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-          const uint32_t off = kk * 32;
-          if (p.terms == 3) {
-            umma_tf32(tmem_base, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, (it | kk) != 0);
-            umma_tf32(tmem_base, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
-            umma_tf32(tmem_base, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, 1);
-          } else {
-            umma_tf32(tmem_base, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, (it | kk) != 0);
+          for (int kk = 0; kk < KS / 8; ++kk) {            // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+            const uint32_t off = kk * 32;
+            const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+            umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
+            if (p.terms == 3) {
+              umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, acc);
+              umma_tf32(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
+            }
           }
+          first = false;
+          tcgen05_commit(&empty[s]);                       // frees the smem slot once these MMAs retire
         }
-        tcgen05_commit(&empty[s]);                         // frees the smem slot once these MMAs retire
+        tcgen05_commit(&acc_full[b]);                      // chunk complete -> epilogue may drain
       }
-      tcgen05_commit(acc_full);                            // accumulator complete
     }
   } else {
     // ===================================================================== epilogue (warps 2..5 -> TMEM lane quarters)
     const int q = warp & 3;                                // this warp may touch TMEM lanes [32q, 32q + 32)
     const int r = q * 32 + lane;                           // accumulator row = pixel within the tile
-    mbar_wait(acc_full, 0);
-    tcgen05_fence_after();
+    float sum[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b = c & 1;
+      mbar_wait(&acc_full[b], (c >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * 2 * BN);
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_main + c0, v);
+        if (p.terms == 3) {
+          uint32_t u[32];
+          tmem_ld32(t_main + BN + c0, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);   // fp32 RN adds
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
+    }
     bool valid;
     long long yoff, rrow, r1pix = 0;
+    int nimg = img;
     if (p.flat) {
       const long long pix = pix0 + r;
       valid = pix < p.total_pix;
       const int HWo = d.OH * d.OW;
       const long long n = pix / HWo;
+      nimg = (int)n;
       const int rem = (int)(pix - n * HWo);
       const int oh = rem / d.OW, ow = rem - oh * d.OW;
       const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
@@ -264,40 +308,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (d.res_mode == TT_RES_UP2_NEAREST) r1pix = ((long long)img * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW;
     }
     if (d.res_mode != TT_RES_UP2_NEAREST) r1pix = rrow;
-    float* yrow = p.y + yoff + d.y_coff;
-    const float* r1 = p.res ? p.res + r1pix * d.res_ld + d.res_coff : nullptr;
-    const float* r2 = p.res2 ? p.res2 + rrow * d.res2_ld + d.res2_coff : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= d.Cout) break;                        // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-      if (!valid) continue;
+    if (valid) {
+      float* yrow = p.y + yoff + d.y_coff;
+      const float* r1 = p.res ? p.res + r1pix * d.res_ld + d.res_coff : nullptr;
+      const float* r2 = p.res2 ? p.res2 + rrow * d.res2_ld + d.res2_coff : nullptr;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = n0 + c0 + j;
-        if (col >= d.Cout) break;
-        float o[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
-        if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-        if (r1) { const float4 t = *reinterpret_cast<const float4*>(r1 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-        if (r2) { const float4 t = *reinterpret_cast<const float4*>(r2 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-        *reinterpret_cast<float4*>(yrow + col) =
-            make_float4(tt_act(o[0], d.act), tt_act(o[1], d.act), tt_act(o[2], d.act), tt_act(o[3], d.act));
+      for (int j = 0; j < BN; j += 4) {
+        const int col = n0 + j;
+        if (col < d.Cout) {
+          float o[4] = {sum[j], sum[j + 1], sum[j + 2], sum[j + 3]};
+          if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)(nimg % d.bias_n_mod) * d.Cout : 0) + col)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+          if (r1) { const float4 t = *reinterpret_cast<const float4*>(r1 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+          if (r2) { const float4 t = *reinterpret_cast<const float4*>(r2 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+          *reinterpret_cast<float4*>(yrow + col) =
+              make_float4(tt_act(o[0], d.act), tt_act(o[1], d.act), tt_act(o[2], d.act), tt_act(o[3], d.act));
+        }
       }
     }
-    tcgen05_fence_before();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                const cuuint32_t* box) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                const cuuint32_t* box, int spatial_stride = 1) {
+  // spatial_stride > 1 (strided convolution): TMA traverses W and H with that element stride, loading
+  // ceil(box / stride) pixels per dimension — the strided im2col gather is done by the copy engine.
+  cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
   CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -315,17 +357,24 @@ inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 }  // namespace
 
 bool tt_conv2d_tc_supported(const tt_conv_desc* d, const void* x, const void* w, const void* y) {
-  if (d->groups != 1 || d->stride != 1) return false;
+  if (d->groups != 1 || (d->stride != 1 && d->stride != 2)) return false;
   if (d->Cin % 4 || d->Cout % 4 || d->x_ld % 4 || d->y_ld % 4 || d->x_nstride % 4 || d->y_nstride % 4) return false;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return false;
   if (d->res_mode != TT_RES_NONE && (d->res_ld % 4)) return false;
   if (d->res2_ld % 4) return false;
-  if (d->OH != (d->H + 2 * d->pad - d->dil * (d->KH - 1)) || d->OW != (d->W + 2 * d->pad - d->dil * (d->KW - 1))) return false;
+  if (d->OH != (d->H + 2 * d->pad - d->dil * (d->KH - 1) - 1) / d->stride + 1 ||
+      d->OW != (d->W + 2 * d->pad - d->dil * (d->KW - 1) - 1) / d->stride + 1) return false;
   return true;
 }
 
+int tt_simt_splits(const tt_conv_desc* d, int has_gather);
+
 extern "C" size_t tt_conv2d_workspace_bytes(const tt_conv_desc* d) {
-  if (!d || d->impl < 2) return 0;
+  if (!d) return 0;
+  if (d->impl < 2) {                                          // SIMT: split-K partial sums for small-M / large-K layers
+    const int s = tt_simt_splits(d, 0);
+    return s > 1 ? (size_t)s * d->N * d->OH * d->OW * d->Cout * 4 : 0;
+  }
   const size_t plane = al256((size_t)d->N * d->H * d->W * d->Cin * 4);
   return (d->impl == 3 ? 2 : 1) * plane;
 }
@@ -353,9 +402,10 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.d = *d;
   a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
   a.terms = terms;
+  a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk
   a.n_slabs = (d->Cin + KS - 1) / KS;
   a.total_pix = d->N * d->OH * d->OW;
-  a.flat = (taps == 1 && d->pad == 0) ? 1 : 0;
+  a.flat = (taps == 1 && d->pad == 0 && d->stride == 1) ? 1 : 0;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int grid_x;
   if (a.flat) {
@@ -370,7 +420,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     // rectangle with TH * TW <= 128 that wastes the fewest rows
     int best_th = 1, best_tw = 1;
     double best = -1;
-    for (int tw = 1; tw <= 128 && tw <= 256; ++tw) {
+    for (int tw = 1; tw <= 128 && tw * d->stride <= 256; ++tw) {
       const int th = 128 / tw;
       if (th < 1) break;
       const double cover = (double)d->OW * d->OH / ((double)tt_cdiv(d->OW, tw) * tw * tt_cdiv(d->OH, th) * th);
@@ -381,9 +431,9 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     a.tiles_w = tt_cdiv(d->OW, a.TW); a.tiles_h = tt_cdiv(d->OH, a.TH);
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t str[3] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)d->W * d->Cin * 4, (cuuint64_t)d->H * d->W * d->Cin * 4};
-    cuuint32_t box[4] = {KS, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
-    if (!encode_map(&ma_hi, a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
-    if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
+    cuuint32_t box[4] = {KS, (cuuint32_t)(a.TW * d->stride), (cuuint32_t)(a.TH * d->stride), 1};
+    if (!encode_map(&ma_hi, a_hi, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
+    if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
     grid_x = a.tiles_w * a.tiles_h * d->N;
   }
   const int BN = d->Cout > 64 ? 128 : 64;

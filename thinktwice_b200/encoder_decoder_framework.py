@@ -128,33 +128,62 @@ class EncoderDecoder(nn.Module):
         return flat, f21, [None, None, f21] + mids, lidar_feat
 
     # ------------------------------------------------------------------ forward (framework:194-210, 238-250)
-    def extract_sensor_feat(self, img, state, img_metas, points):
+    def stage(self, batch):
+        """Host half of forward_inference: everything that touches host data (state vector, img_metas matrices) is
+        computed here and uploaded into static device buffers, so the device half is a fixed launch sequence."""
         e = self.eng
-        cam = self.img_encoder(img=img, img_metas=img_metas)
+        img = batch['img']
+        if img.dim() == 5:
+            img = img.unsqueeze(1)
+        B, T, N = img.shape[:3]
+        speed = batch['speed'].to(dtype=torch.float32).view(-1, 1) / 12.
+        st = torch.cat([speed, batch['target_point'].to(torch.float32), batch['target_command'].to(torch.float32)], -1)
+        e.upload('in.state', torch.cat([st, st.new_zeros(B, 3)], 1).contiguous())      # 9 -> 12 columns (vector loads)
+        e.upload('in.img', img)
+        e.upload('in.points', batch['points'][:, -1].contiguous())
+        lidar2img, ida = self.img_encoder.stage(batch['img_metas'], B, T, N)
+        self.decoder.stage(lidar2img, ida)
+        return (B, T, N, tuple(img.shape), tuple(batch['points'].shape))
+
+    def _device_forward(self):
+        """Device half: extract_sensor_feat (framework:238-250) + get_fusion_feat + decoder, kernels only."""
+        e = self.eng
+        cam = self.img_encoder.forward_device(e.static('in.img'))
         cam['bev'] = e.anti_transpose(cam['bev'], 'cam.bev.at')     # rot90(flip): match the Roach BEV
-        st = torch.cat(state[:3], dim=-1).float()
-        st = torch.cat([st, st.new_zeros(st.shape[0], 3)], 1).contiguous()
+        st = e.static('in.state')
         m = e.linear(e.wrap(st.view(-1, 1, 1, 12)), self.w['meas0'], name='meas.h', act=ACT_RELU)
         meas = e.linear(m, self.w['meas2'], name='meas', act=ACT_RELU)
-        lidar = self.lidar_encoder(points[:, -1, ...])
-        return cam, lidar, meas
+        lidar = self.lidar_encoder(e.static('in.points'))
+        flat, bev32, mid, lidar_hi = self.get_fusion_feat(cam['bev'], lidar[0])
+        pred = self.decoder(flat, bev32, meas, None, self, None, [None, None, cam['fpn_feats'], lidar_hi])
+        self.last_cam_feat = cam                                   # cam['seg'] etc. for parity checks
+        return pred
+
+    def enable_cuda_graph(self, flag=True):
+        """Replay the device half as one CUDA graph (no per-kernel host launch cost).  The graph is captured on
+        the first forward after this call (after one eager warm-up that allocates every buffer)."""
+        self.use_graph = flag
+        self._graphs = {}
+        return self
 
     @torch.no_grad()
     def forward_inference(self, batch):
         if self.eng is None:
-            self.prepare(batch['img'].device)
-        dev = self.eng.device
+            self.prepare(batch['img'].device if batch['img'].is_cuda else 'cuda:0')
         self.epoch = 10000
-        target_point = batch['target_point'].to(dev, dtype=torch.float32)
-        command = batch['target_command'].to(dev, dtype=torch.float32)
-        speed = batch['speed'].to(dev, dtype=torch.float32).view(-1, 1) / 12.
-        state = [speed, target_point, command, batch.get('target_command_raw')]
-        cam, lidar, meas = self.extract_sensor_feat(batch['img'].to(dev), state, batch['img_metas'], batch['points'].to(dev))
-        flat, bev32, mid, lidar_hi = self.get_fusion_feat(cam['bev'], lidar[0])
-        pred = self.decoder(flat, bev32, meas, target_point, self, None,
-                            [cam['lidar2img'], cam['ida_mat'], cam['fpn_feats'], lidar_hi])
-        self.last_cam_feat = cam                                   # cam['seg'] etc. for parity checks
-        return pred
+        key = self.stage(batch)
+        if not getattr(self, 'use_graph', False):
+            return self._device_forward()
+        g = self._graphs.get(key)
+        if g is None:
+            self._device_forward()                                 # eager warm-up: allocates all persistent buffers
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                pred = self._device_forward()
+            g = self._graphs[key] = (graph, pred)
+        g[0].replay()
+        return g[1].fresh()
 
     def forward(self, is_eval=True, **kwargs):
         raise NotImplementedError('training / loss path is out of scope (SURVEY.md §8f f4); use forward_inference')

@@ -57,6 +57,7 @@ class Engine:
         self.bufs = {}
         self.tc_ws = None           # grow-only workspace of the tcgen05 path (TF32 split planes)
         self.tc_min_rows = 512
+        self.tc_strides = (1, 2)
         self.prof = None            # bench.py: list of (name, flops, start_event, end_event) per conv launch
         lib.load()
 
@@ -69,6 +70,18 @@ class Engine:
             self.bufs[key] = t
         return t
 
+    def upload(self, name, t):
+        """copy a host (or device) tensor into the persistent device buffer `name` (static address: graph-safe)."""
+        b = self.buf(name, t.shape, t.dtype)
+        b.copy_(t, non_blocking=True)
+        return b
+
+    def static(self, name):
+        for (n, _, _), t in self.bufs.items():
+            if n == name:
+                return t
+        raise KeyError(f'static buffer {name} has not been staged')
+
     def fmap(self, name, N, H, W, C, ld=None, zero=False):
         ld = ld if ld is not None else C
         return FMap(self.buf(name, (N, H, W, ld), zero=zero), N, H, W, C, ld, 0)
@@ -80,7 +93,7 @@ class Engine:
 
     # ------------------------------------------------------------------ conv / linear
     def conv(self, x, pw, out=None, name=None, stride=1, pad=0, dil=1, act=0, res=None, res_mode=0, res2=None,
-             scatter=None, out_ld=None, impl=None, x_nstride=0, y_nstride=0, n_images=None):
+             scatter=None, out_ld=None, impl=None, x_nstride=0, y_nstride=0, n_images=None, bias_n_mod=0):
         """y = act(conv(x) + bias + res + res2).  `out` (FMap) selects the destination (concat slice / scatter
         target); otherwise a buffer `name` is created.  scatter = (oy_mul, oy_add, ox_mul, ox_add)."""
         assert x.C == pw.Cin, (x.C, pw.Cin, name)
@@ -100,6 +113,7 @@ class Engine:
         else:
             d.oy_mul, d.oy_add, d.ox_mul, d.ox_add = scatter
         d.act = act
+        d.bias_n_mod = bias_n_mod
         d.res_mode = res_mode if res is not None else 0
         if res is not None:
             if d.res_mode == 0:
@@ -110,15 +124,15 @@ class Engine:
             d.res2_ld, d.res2_coff = res2.ld, 0
         impl = self.impl if impl is None else impl
         # tcgen05 path: dense stride-1 convs with enough work to fill 128-row tiles; everything else stays SIMT fp32
-        use_tc = (impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and stride == 1 and pw.groups == 1
+        use_tc = (impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and stride in self.tc_strides and pw.groups == 1
                   and x.ld % 4 == 0 and x.coff % 4 == 0 and out.ld % 4 == 0 and out.coff % 4 == 0
                   and (res is None or (res.ld % 4 == 0 and res.coff % 4 == 0)) and (res2 is None or (res2.ld % 4 == 0 and res2.coff % 4 == 0))
                   and x_nstride % 4 == 0 and y_nstride % 4 == 0
                   and d.N * OH * OW >= self.tc_min_rows and pw.Cout >= 32)
         d.impl = impl if use_tc else lib.IMPL_SIMT
         ws = None
-        if use_tc:
-            need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))
+        need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # TC: TF32 split planes; SIMT: split-K partials (or 0)
+        if need:
             if self.tc_ws is None or self.tc_ws.numel() < need:
                 self.tc_ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
             ws = self.tc_ws

@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
                [('x_nstride', C.c_longlong), ('y_nstride', C.c_longlong)] + \
                [(n, C.c_int) for n in ('Cout', 'KH', 'KW', 'stride', 'pad', 'dil', 'groups', 'OH', 'OW',
                                         'y_ld', 'y_coff', 'yH', 'yW', 'oy_mul', 'oy_add', 'ox_mul', 'ox_add',
-                                        'act', 'res_mode', 'res_ld', 'res_coff', 'res_H', 'res_W',
+                                        'act', 'bias_n_mod', 'res_mode', 'res_ld', 'res_coff', 'res_H', 'res_W',
                                         'res2_ld', 'res2_coff', 'taps', 'M', 'impl')]
 
 

@@ -222,23 +222,20 @@ class LSS:
             x = e.conv(x, w['s2f'][i], out=out if last else None, name=f's2f.{i}', stride=s, pad=k // 2, act=ACT_RELU)
         return x
 
-    def _single_sweep(self, imgs, mats, sweep_index, bev_out):
-        """lss.py:542-621 for one sweep; imgs (B, N, 3, H, W) NCHW on the device."""
+    def _single_sweep(self, imgs, s, bev_out):
+        """lss.py:542-621 for one sweep; imgs (B, N, 3, H, W) NCHW on the device; s = sweep distance from the key frame."""
         e, w = self.eng, self.w
         B, N = imgs.shape[:2]
         x = e.nchw_to_nhwc(imgs.reshape(B * N, *imgs.shape[2:]), 'img.nhwc', cpad=4)
         fpn = self._pafpn(self._backbone(x))
         src = e.conv(fpn[2], w['neck_conv'], name='img_feats')
-        mlp_in = e.wrap(self.depthnet_mlp_input(mats).to(e.device).view(B * N, 1, 1, 24))
+        mlp_in = e.wrap(e.static('in.mlp_in').view(B * N, 1, 1, 24))
         merge_in = e.fmap('merge_in', B * N, src.H, src.W, self.output_channels + 128)
         depth = self._depthnet(src, mlp_in, merge_in)
         seg = self._unet(fpn)
         self._seg_to_feat(seg, merge_in.slice(self.output_channels, 128))
         feat = e.conv(merge_in, w['merge'], name='img_feature', pad=1)
-        # geometry matrices (lss.py:496, 502) on the host in fp32, as torch does it
-        ida_inv = torch.inverse(mats['ida_mats'][:, sweep_index])
-        comb = mats['sensor2ego_mats'][:, sweep_index].matmul(torch.inverse(mats['intrin_mats'][:, sweep_index]))
-        m = torch.stack([ida_inv, comb], 2).reshape(B * N, 32).contiguous().to(e.device)
+        m = e.static(f'in.lift_mats.{s}')                           # staged by stage(): ida^-1 and sensor2ego @ intrin^-1
         d = LiftSplatDesc()
         d.B, d.N, d.D, d.fH, d.fW, d.C = B, N, self.depth_channels, src.H, src.W, self.output_channels
         d.ld_d, d.d_coff, d.ld_c, d.c_coff = depth.ld, 0, feat.ld, 0
@@ -251,25 +248,42 @@ class LSS:
         return dict(fpn_feats=fpn, depth=depth, seg=seg, img_feature=feat)
 
     # ------------------------------------------------------------------ forward (lss.py:635-724)
-    def forward(self, img, img_metas, timestamps=None, is_return_depth=False):
+    def stage(self, img_metas, B, T, N):
+        """Host half of LSS.forward: the python loops over img_metas (lss.py:667-687), the 4x4 inverses of
+        get_geometry (lss.py:496,502) and DepthNet's 22 camera scalars (lss.py:206-231), uploaded into static
+        device buffers.  Tiny, input-derived, and kept off the device path so the forward is graph-capturable."""
         e = self.eng
-        if img.dim() == 5:
-            img = img.unsqueeze(1)
+        mats = self.build_mats(img_metas, N)
+        e.upload('in.mlp_in', self.depthnet_mlp_input(mats).contiguous())
+        for s in range(T):
+            idx = -1 if s == 0 else -s                              # key frame -> -1; history sweep s -> mats[-s] (lss.py:712-716)
+            ida_inv = torch.inverse(mats['ida_mats'][:, idx])
+            comb = mats['sensor2ego_mats'][:, idx].matmul(torch.inverse(mats['intrin_mats'][:, idx]))
+            e.upload(f'in.lift_mats.{s}', torch.stack([ida_inv, comb], 2).reshape(B * N, 32).contiguous())
+        return (torch.stack([m[-1]['lidar2img'] for m in img_metas], 0).float(), mats['ida_mats'][:, -1].clone())
+
+    def forward_device(self, img):
+        """Device half: img (B, T, N, 3, H, W) fp32 resident on the GPU."""
+        e = self.eng
         B, T, N = img.shape[:3]
         assert T == self.queue_len, 'LSS.queue_len must be set correctly in config!'
-        mats = self.build_mats(img_metas, N)
         X, Y = int(self.voxel_num[0]), int(self.voxel_num[1])
         bev_cat = e.fmap('bev_cat', B, Y, X, self.output_channels * T)
         # history sweeps first (their buffers are recycled), key frame last so its FPN maps stay live.
-        # bev_feature_list = [key, sweep 1, ...] (lss.py:697,717); sweep s uses mats[-s] (lss.py:712-716)
+        # bev_feature_list = [key, sweep 1, ...] (lss.py:697,717)
         for s in range(T - 1, 0, -1):
-            self._single_sweep(img[:, T - 1 - s], mats, -s, bev_cat.slice(self.output_channels * s, self.output_channels))
-        key = self._single_sweep(img[:, T - 1], mats, -1, bev_cat.slice(0, self.output_channels))
+            self._single_sweep(img[:, T - 1 - s], s, bev_cat.slice(self.output_channels * s, self.output_channels))
+        key = self._single_sweep(img[:, T - 1], 0, bev_cat.slice(0, self.output_channels))
         bev = e.conv(bev_cat, self.w['sweep_merge'], name='bev', pad=1) if T > 1 else bev_cat
-        outs = dict(bev=bev, seg=key['seg'], depth=key['depth'], fpn_feats=key['fpn_feats'],
-                    img_feature=key['img_feature'])
-        outs['lidar2img'] = torch.stack([m[-1]['lidar2img'] for m in img_metas], 0).float()
-        outs['ida_mat'] = mats['ida_mats'][:, -1].clone()
+        return dict(bev=bev, seg=key['seg'], depth=key['depth'], fpn_feats=key['fpn_feats'], img_feature=key['img_feature'])
+
+    def forward(self, img, img_metas, timestamps=None, is_return_depth=False):
+        if img.dim() == 5:
+            img = img.unsqueeze(1)
+        B, T, N = img.shape[:3]
+        lidar2img, ida = self.stage(img_metas, B, T, N)
+        outs = self.forward_device(img.to(self.eng.device))
+        outs['lidar2img'], outs['ida_mat'] = lidar2img, ida
         return outs
 
     __call__ = forward

@@ -24,11 +24,16 @@ class LazyPred(dict):
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
-        self._lazy = {}
+        self._lazy, self._all_lazy, self._made = {}, {}, set()
+
+    def lazy(self, key, fn):
+        self._lazy[key] = fn
+        self._all_lazy[key] = fn
 
     def __missing__(self, key):
         if key in self._lazy:
             self[key] = self._lazy.pop(key)()
+            self._made.add(key)
             return self[key]
         raise KeyError(key)
 
@@ -37,6 +42,13 @@ class LazyPred(dict):
 
     def keys(self):
         return list(dict.keys(self)) + list(self._lazy.keys())
+
+    def fresh(self):
+        """new view over the same (static) output buffers with every lazy entry un-materialised (graph replays)."""
+        o = LazyPred({k: v for k, v in dict.items(self) if k not in self._made})
+        o._lazy = dict(self._all_lazy)
+        o._all_lazy, o._made = self._all_lazy, set()
+        return o
 
 
 @HEADS.register_module()
@@ -79,8 +91,9 @@ class ThinkTwiceDecoder:
             L['aw'] = pk.linear(c + 'deformable_attention.attention_weights')
             # value_proj(x + cams_embeds[cam] + level_embeds[lvl]) = W x + (W (e_cam + e_lvl) + b): one bias per (cam, lvl)
             Wv, bv = pk.sd[c + 'deformable_attention.value_proj.weight'].double(), pk.sd[c + 'deformable_attention.value_proj.bias'].double()
-            L['value'] = [[pk.linear(c + 'deformable_attention.value_proj', bias=(bv + Wv @ (cams[cam] + lvls[l])).float())
-                           for l in range(4)] for cam in range(4)]
+            L['value'] = [pk.linear(c + 'deformable_attention.value_proj',
+                                    bias=torch.stack([bv + Wv @ (cams[cam] + lvls[l]) for cam in range(4)]).float().reshape(-1))
+                          for l in range(4)]                     # per level: bias table [4 cams][256] (bias_n_mod = 4)
             L['ffn_ln'] = (pk.vec(c + 'ffn.norm.weight'), pk.vec(c + 'ffn.norm.bias'))
             L['ffn1'], L['ffn2'] = pk.linear(c + 'ffn.w_1'), pk.linear(c + 'ffn.w_2')
             L['op_ln'] = (pk.vec(c + 'output_proj.0.weight'), pk.vec(c + 'output_proj.0.bias'))
@@ -92,6 +105,12 @@ class ThinkTwiceDecoder:
             L['bev_up'] = (pk.conv(q + 'BEV_feat_update_module.0'), pk.conv(q + 'BEV_feat_update_module.2'))
             L['flat_up'] = (pk.linear(q + 'flattened_BEV_feat_update_module.0'), pk.linear(q + 'flattened_BEV_feat_update_module.2'))
             self.layers.append(L)
+
+    def stage(self, lidar2img, ida):
+        """host half: upload the (B, 4, 4, 4) projection matrices the Look module needs."""
+        B = lidar2img.shape[0]
+        self.eng.upload('look.l2i', lidar2img.reshape(B, 4, 16).float().contiguous())
+        self.eng.upload('look.ida', ida.reshape(B, 4, 16).float().contiguous())
 
     # ------------------------------------------------------------------ helpers
     def _seq(self, x, ws, tag, last_act=ACT_NONE, out=None):
@@ -146,12 +165,9 @@ class ThinkTwiceDecoder:
         # value_proj over all keys of every (cam, level) with the embedding folded into the bias (msda:474)
         nk = meta['num_keys']
         value = e.buf('look.value', (B * cams, nk, 256))
-        for l, m in enumerate(mlvl):
-            hw = m.H * m.W
-            for cam in range(cams):
-                xin = FMap(m.t, B, m.H, m.W, 256, 256, cam * hw * 256)
-                out = FMap(value, B, m.H, m.W, 256, 256, (cam * nk + meta['lvl_start'][l]) * 256)
-                e.conv(xin, L['value'][cam][l], out=out, name=f'look.value{l}{cam}', x_nstride=cams * hw * 256, y_nstride=cams * nk * 256)
+        for l, m in enumerate(mlvl):                                 # one launch per level over all B*cams images
+            out = FMap(value, B * cams, m.H, m.W, 256, 256, meta['lvl_start'][l] * 256)
+            e.conv(m, L['value'][l], out=out, name=f'look.value{l}', y_nstride=nk * 256, bias_n_mod=cams)
         off = e.linear(q, L['off'], name='look.off')
         aw = e.linear(q, L['aw'], name='look.aw')
         att = e.fmap('look.att', B * cams * cap, 1, 1, 256)
@@ -196,7 +212,7 @@ class ThinkTwiceDecoder:
 
         # ---- Look-module inputs (thinktwice_decoder.py:442-450)
         mlvl = [e.conv(fpn[i], w['fpn_linear'][i], name=f'dec.mlvl{i}') for i in range(4)]
-        meta = self._look_meta(B, mlvl, lidar2img, ida)
+        meta = self._look_meta(B, mlvl)
 
         cur_bev, cur_flat = bev, flat
         s_bev, s_flat, s_fut = [], [], []
@@ -243,16 +259,16 @@ class ThinkTwiceDecoder:
         o['mu_branches'], o['sigma_branches'] = cs[:, :, 0, :2], cs[:, :, 0, 2:]
         o['future_mu'], o['future_sigma'] = cs[:, :, 1:, :2], cs[:, :, 1:, 2:]
         H, W = bev.H, bev.W
-        o._lazy['bev_feature'] = lambda: bev.nchw()
-        o._lazy['refine_flattned_BEV_feature'] = lambda: torch.stack([f.t.view(B, 256) for f in s_flat], 1)
-        o._lazy['refine_BEV_feature'] = lambda: torch.stack([f.nchw() for f in s_bev], 1)
-        o._lazy['refine_future_BEV_feature'] = lambda: torch.stack(
-            [f.nchw().reshape(B, T, 32, H, W) for f in s_fut], 1).reshape(B, T, K, 32, H, W).transpose(1, 2)   # quirky view (:481)
+        o.lazy('bev_feature', lambda: bev.nchw())
+        o.lazy('refine_flattned_BEV_feature', lambda: torch.stack([f.t.view(B, 256) for f in s_flat], 1))
+        o.lazy('refine_BEV_feature', lambda: torch.stack([f.nchw() for f in s_bev], 1))
+        o.lazy('refine_future_BEV_feature', lambda: torch.stack(
+            [f.nchw().reshape(B, T, 32, H, W) for f in s_fut], 1).reshape(B, T, K, 32, H, W).transpose(1, 2))  # quirky view (:481)
         return o
 
     __call__ = forward
 
-    def _look_meta(self, B, mlvl, lidar2img, ida):
+    def _look_meta(self, B, mlvl):
         e = self.eng
         H_img, W_img = self.config['img_size']
         d = LookDesc()
@@ -266,6 +282,5 @@ class ThinkTwiceDecoder:
         md = MsdaDesc()
         md.BN, md.rows_cap, md.heads, md.levels, md.points, md.dh = B * 4, NQ, 8, 4, 8, 32
         md.lvl_h, md.lvl_w, md.lvl_start, md.num_keys = d.lvl_h, d.lvl_w, lib.i4(starts), acc
-        l2i = e.buf('look.l2i', (B, 4, 16)); l2i.copy_(lidar2img.reshape(B, 4, 16).float())
-        idm = e.buf('look.ida', (B, 4, 16)); idm.copy_(ida.reshape(B, 4, 16).float())
+        l2i, idm = e.static('look.l2i'), e.static('look.ida')      # staged by stage()
         return dict(B=B, look_desc=d, msda_desc=md, l2i=l2i, ida=idm, num_keys=acc, lvl_start=starts)

@@ -78,6 +78,8 @@ class Packer:
         w = (self.sd[n + '.weight'] if weight is None else weight).double()
         b = self.sd.get(n + '.bias') if bias is None else bias
         b = b.double() if b is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+        if b.numel() != w.shape[0]:                                 # per-image bias table: no folding allowed
+            assert in_affine is None and bn_after is None
         if in_affine is not None:
             s, t = in_affine
             b = b + w @ t
