@@ -296,7 +296,8 @@ def test_voxelize_mean_matches_oracle(eng):
     ws = torch.empty(lib.load().tt_voxelize_workspace_bytes(C.byref(d)), dtype=torch.uint8, device='cuda')
     feats, coords = torch.zeros(B * P, 5, device='cuda'), torch.zeros(B * P, 4, dtype=torch.int32, device='cuda')
     count = torch.zeros(1, dtype=torch.int32, device='cuda')
-    lib.call('tt_voxelize_mean', C.byref(d), _p(pts.cuda().contiguous()), _p(feats), _p(coords), _p(count), _p(ws))
+    dpts = pts.cuda().contiguous()
+    lib.call('tt_voxelize_mean', C.byref(d), _p(dpts), _p(feats), _p(coords), _p(count), _p(ws))
     n = int(count.item())
     got = {tuple(c.tolist()): f for c, f in zip(coords[:n].cpu(), feats[:n].cpu())}
     exp = {}
@@ -383,5 +384,6 @@ def test_msda_matches_oracle(eng):
     d.lvl_start, d.num_keys = lib.i4(starts), nk
     out = torch.zeros(BN * cap, heads * dh, device='cuda')
     ml = torch.tensor([cap], dtype=torch.int32, device='cuda')
-    lib.call('tt_msda_forward', C.byref(d), _p(value.cuda()), _p(off.cuda()), _p(logits.cuda()), _p(ref_pts.cuda()), _p(ml), _p(out))
+    dv, do, dl, dr = value.cuda(), off.cuda(), logits.cuda(), ref_pts.cuda()      # keep alive across the call
+    lib.call('tt_msda_forward', C.byref(d), _p(dv), _p(do), _p(dl), _p(dr), _p(ml), _p(out))
     assert relerr(out.view(BN, cap, heads * dh), ref) < 1e-4

@@ -283,47 +283,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
     }
-    bool valid;
-    long long yoff, rrow, r1pix = 0;
-    int nimg = img;
-    if (p.flat) {
-      const long long pix = pix0 + r;
-      valid = pix < p.total_pix;
-      const int HWo = d.OH * d.OW;
-      const long long n = pix / HWo;
-      nimg = (int)n;
-      const int rem = (int)(pix - n * HWo);
-      const int oh = rem / d.OW, ow = rem - oh * d.OW;
-      const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
-      yoff = n * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
-      rrow = pix;
-      if (d.res_mode == TT_RES_UP2_NEAREST) r1pix = (n * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW;
-    } else {
-      const int th = r / p.TW, tw = r - th * p.TW;
-      const int oh = oh0 + th, ow = ow0 + tw;
-      valid = (r < p.TH * p.TW) && oh < d.OH && ow < d.OW;
-      const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
-      yoff = img * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
-      rrow = ((long long)img * d.OH + oh) * d.OW + ow;
-      if (d.res_mode == TT_RES_UP2_NEAREST) r1pix = ((long long)img * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW;
-    }
-    if (d.res_mode != TT_RES_UP2_NEAREST) r1pix = rrow;
-    if (valid) {
-      float* yrow = p.y + yoff + d.y_coff;
-      const float* r1 = p.res ? p.res + r1pix * d.res_ld + d.res_coff : nullptr;
-      const float* r2 = p.res2 ? p.res2 + rrow * d.res2_ld + d.res2_coff : nullptr;
+    // ---- coalesced store: transpose the 128 x BN tile through shared memory (the operand ring is idle now: every
+    // TMA load has been consumed and every MMA has retired once the last acc_full fired), then each warp writes
+    // whole channels-last rows — 32 lanes x float4 = 512 contiguous bytes per instruction instead of 32 scattered
+    // 16-byte stores.  Row pitch BN + 4 floats keeps both the column-wise writes and the row-wise reads conflict-free.
+    constexpr int PITCH = BN + 4;
+    float* tile = reinterpret_cast<float*>(smem);
 #pragma unroll
-      for (int j = 0; j < BN; j += 4) {
-        const int col = n0 + j;
-        if (col < d.Cout) {
-          float o[4] = {sum[j], sum[j + 1], sum[j + 2], sum[j + 3]};
-          if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)(nimg % d.bias_n_mod) * d.Cout : 0) + col)); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-          if (r1) { const float4 t = *reinterpret_cast<const float4*>(r1 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-          if (r2) { const float4 t = *reinterpret_cast<const float4*>(r2 + col); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
-          *reinterpret_cast<float4*>(yrow + col) =
-              make_float4(tt_act(o[0], d.act), tt_act(o[1], d.act), tt_act(o[2], d.act), tt_act(o[3], d.act));
-        }
+    for (int j = 0; j < BN; j += 4)
+      *reinterpret_cast<float4*>(&tile[r * PITCH + j]) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
+    constexpr int LPR = BN / 4;                              // lanes per row
+    constexpr int RPI = 32 / LPR;                            // rows per warp instruction (1 at BN = 128, 2 at BN = 64)
+    const int sub = lane / LPR, cl = (lane % LPR) * 4;
+    const int col = n0 + cl;
+    const bool col_ok = col < d.Cout;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+    const int HWo = d.OH * d.OW;
+#pragma unroll 4
+    for (int i = 0; i < 32; i += RPI) {
+      const int rr = q * 32 + i + sub;
+      bool valid;
+      long long yoff, rrow, r1pix;
+      int nimg, oh, ow;
+      if (p.flat) {
+        const long long pix = pix0 + rr;
+        valid = pix < p.total_pix;
+        nimg = (int)(pix / HWo);
+        const int rem = (int)(pix - (long long)nimg * HWo);
+        oh = rem / d.OW; ow = rem - oh * d.OW;
+        rrow = pix;
+      } else {
+        const int th = rr / p.TW, tw = rr - th * p.TW;
+        oh = oh0 + th; ow = ow0 + tw;
+        nimg = img;
+        valid = (rr < p.TH * p.TW) && oh < d.OH && ow < d.OW;
+        rrow = ((long long)img * d.OH + oh) * d.OW + ow;
       }
+      if (!valid || !col_ok) continue;
+      yoff = nimg * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
+      r1pix = d.res_mode == TT_RES_UP2_NEAREST
+                  ? ((long long)nimg * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW
+                  : rrow;
+      const float4 t = *reinterpret_cast<const float4*>(&tile[rr * PITCH + cl]);
+      float o[4] = {t.x, t.y, t.z, t.w};
+      if (p.bias) {
+        bv = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)(nimg % d.bias_n_mod) * d.Cout : 0) + col));
+        o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+      }
+      if (p.res) { const float4 u = *reinterpret_cast<const float4*>(p.res + r1pix * d.res_ld + d.res_coff + col); o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w; }
+      if (p.res2) { const float4 u = *reinterpret_cast<const float4*>(p.res2 + rrow * d.res2_ld + d.res2_coff + col); o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w; }
+      *reinterpret_cast<float4*>(p.y + yoff + d.y_coff + col) =
+          make_float4(tt_act(o[0], d.act), tt_act(o[1], d.act), tt_act(o[2], d.act), tt_act(o[3], d.act));
     }
   }
   tcgen05_fence_before();
