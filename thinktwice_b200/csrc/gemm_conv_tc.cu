@@ -118,6 +118,7 @@ struct TcArgs {
   int terms;             // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi only
   int chunk;             // K slabs accumulated inside TMEM before the epilogue folds them into fp32 registers
   int total_pix;         // N * OH * OW
+  int m_tiles, n_tiles;  // persistent tile walk: tile t -> (m tile t / n_tiles, n tile t % n_tiles)
 };
 
 // operand split: hi = RN_tf32(x), lo = RN_tf32(x - hi); both exactly representable in TF32, so the tensor core's
@@ -144,6 +145,9 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long lo
   }
 }
 
+// Persistent, warp-specialised kernel: each CTA (one per SM) walks tiles t = blockIdx.x, += gridDim.x.  The smem
+// ring, the TMEM ping-pong and all phase counters run ACROSS tiles, so while the epilogue warps store tile i the
+// TMA and MMA warps are already deep into tile i + 1.
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -153,8 +157,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr int B_BYTES = BN * KS * 4;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr int TMEM_COLS = 4 * BN;                       // 2 (ping-pong) x {main, corr} x BN fp32 columns
+  constexpr int PITCH = 36;                               // epilogue slab: 128 rows x 32 columns (+4 pad: conflict-free)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* tile = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);                  // [128][36]
+  long long* row_y = reinterpret_cast<long long*>(tile + BM * PITCH);                   // [128] output offset of row
+  long long* row_r1 = row_y + BM;                                                       // [128] residual-1 pixel
+  long long* row_r2 = row_r1 + BM;                                                      // [128] residual-2 pixel (= GEMM row)
+  int* row_flag = reinterpret_cast<int*>(row_r2 + BM);                                  // [128] valid | image << 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(row_flag + BM);
   uint64_t* full = bars;                                  // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + STAGES;                        // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;                 // [2]       MMA -> epilogue (chunk finished)
@@ -163,22 +173,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const tt_conv_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int img, oh0, ow0;
-  long long pix0 = 0;
-  if (p.flat) {
-    img = 0; oh0 = 0; ow0 = 0;
-    pix0 = (long long)blockIdx.x * BM;
-  } else {
-    const int tw = blockIdx.x % p.tiles_w;
-    const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
-    img = blockIdx.x / (p.tiles_w * p.tiles_h);
-    oh0 = th * p.TH;
-    ow0 = tw * p.TW;
-  }
-  const int n0 = blockIdx.y * BN;
   const int taps = d.KH * d.KW;
   const int k_iters = taps * p.n_slabs;
   const int n_chunks = (k_iters + p.chunk - 1) / p.chunk;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -199,22 +197,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KS * 4;   // bytes one activation box delivers
       const uint32_t tx = (p.terms == 3 ? 2 : 1) * (a_box + B_BYTES);
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        const int tap = it / p.n_slabs, slab = it - tap * p.n_slabs;
-        const int kh = tap / d.KW, kw = tap - kh * d.KW;
-        mbar_expect_tx(&full[s], tx);
-        int cw, ch, cn;
-        if (p.flat) { cw = (int)pix0; ch = 0; cn = 0; }
-        else { cw = ow0 * d.stride - d.pad + kw * d.dil; ch = oh0 * d.stride - d.pad + kh * d.dil; cn = img; }
-        tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
-        tma_load_3d(st + 2 * A_BYTES, &map_b_hi, &full[s], slab * KS, tap, n0);
-        if (p.terms == 3) {
-          tma_load_4d(st + A_BYTES, &map_a_lo, &full[s], slab * KS, cw, ch, cn);
-          tma_load_3d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, &full[s], slab * KS, tap, n0);
+      int ig = 0;                                                               // ring position, continues across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int n0 = nt * BN;
+        int cw0, ch0, cn;
+        if (p.flat) { cw0 = mt * BM; ch0 = 0; cn = 0; }
+        else {
+          const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h;
+          cn = mt / (p.tiles_w * p.tiles_h);
+          cw0 = tw * p.TW * d.stride - d.pad; ch0 = th * p.TH * d.stride - d.pad;
+        }
+        for (int it = 0; it < k_iters; ++it, ++ig) {
+          const int s = ig % STAGES;
+          mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          const int tap = it / p.n_slabs, slab = it - tap * p.n_slabs;
+          const int kh = tap / d.KW, kw = tap - kh * d.KW;
+          mbar_expect_tx(&full[s], tx);
+          const int cw = p.flat ? cw0 : cw0 + kw * d.dil, ch = p.flat ? 0 : ch0 + kh * d.dil;
+          tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
+          tma_load_3d(st + 2 * A_BYTES, &map_b_hi, &full[s], slab * KS, tap, n0);
+          if (p.terms == 3) {
+            tma_load_4d(st + A_BYTES, &map_a_lo, &full[s], slab * KS, cw, ch, cn);
+            tma_load_3d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, &full[s], slab * KS, tap, n0);
+          }
         }
       }
     }
@@ -222,120 +229,143 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      int it = 0;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int b = c & 1;
-        mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);        // epilogue has drained this accumulator pair
-        tcgen05_fence_after();
-        const uint32_t t_main = tmem_base + (uint32_t)(b * 2 * BN), t_corr = t_main + BN;
-        const int it_end = min(it + p.chunk, k_iters);
-        bool first = true;
-        for (; it < it_end; ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full[s], (it / STAGES) & 1);
+      int ig = 0, cg = 0;                                                       // ring / chunk counters across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int it = 0;
+        for (int c = 0; c < n_chunks; ++c, ++cg) {
+          const int b = cg & 1;
+          mbar_wait(&acc_empty[b], ((cg >> 1) & 1) ^ 1);     // epilogue has drained this accumulator pair
           tcgen05_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+          const uint32_t t_main = tmem_base + (uint32_t)(b * 2 * BN), t_corr = t_main + BN;
+          const int it_end = min(it + p.chunk, k_iters);
+          bool first = true;
+          for (; it < it_end; ++it, ++ig) {
+            const int s = ig % STAGES;
+            mbar_wait(&full[s], (ig / STAGES) & 1);
+            tcgen05_fence_after();
+            const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < KS / 8; ++kk) {            // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-            const uint32_t off = kk * 32;
-            const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-            umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
-            if (p.terms == 3) {
-              umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, acc);
-              umma_tf32(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
+            for (int kk = 0; kk < KS / 8; ++kk) {            // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+              const uint32_t off = kk * 32;
+              const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+              umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
+              if (p.terms == 3) {
+                umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, acc);
+                umma_tf32(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
+              }
             }
+            first = false;
+            tcgen05_commit(&empty[s]);                       // frees the smem slot once these MMAs retire
           }
-          first = false;
-          tcgen05_commit(&empty[s]);                       // frees the smem slot once these MMAs retire
+          tcgen05_commit(&acc_full[b]);                      // chunk complete -> epilogue may drain
         }
-        tcgen05_commit(&acc_full[b]);                      // chunk complete -> epilogue may drain
       }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5 -> TMEM lane quarters)
     const int q = warp & 3;                                // this warp may touch TMEM lanes [32q, 32q + 32)
     const int r = q * 32 + lane;                           // accumulator row = pixel within the tile
-    float sum[BN];
-#pragma unroll
-    for (int j = 0; j < BN; ++j) sum[j] = 0.f;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    for (int c = 0; c < n_chunks; ++c) {
-      const int b = c & 1;
-      mbar_wait(&acc_full[b], (c >> 1) & 1);
-      tcgen05_fence_after();
-      const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * 2 * BN);
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_main + c0, v);
-        if (p.terms == 3) {
-          uint32_t u[32];
-          tmem_ld32(t_main + BN + c0, u);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);   // fp32 RN adds
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
-    }
-    // ---- coalesced store: transpose the 128 x BN tile through shared memory (the operand ring is idle now: every
-    // TMA load has been consumed and every MMA has retired once the last acc_full fired), then each warp writes
-    // whole channels-last rows — 32 lanes x float4 = 512 contiguous bytes per instruction instead of 32 scattered
-    // 16-byte stores.  Row pitch BN + 4 floats keeps both the column-wise writes and the row-wise reads conflict-free.
-    constexpr int PITCH = BN + 4;
-    float* tile = reinterpret_cast<float*>(smem);
-#pragma unroll
-    for (int j = 0; j < BN; j += 4)
-      *reinterpret_cast<float4*>(&tile[r * PITCH + j]) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
-    asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
-    constexpr int LPR = BN / 4;                              // lanes per row
-    constexpr int RPI = 32 / LPR;                            // rows per warp instruction (1 at BN = 128, 2 at BN = 64)
-    const int sub = lane / LPR, cl = (lane % LPR) * 4;
-    const int col = n0 + cl;
-    const bool col_ok = col < d.Cout;
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
     const int HWo = d.OH * d.OW;
-#pragma unroll 4
-    for (int i = 0; i < 32; i += RPI) {
-      const int rr = q * 32 + i + sub;
-      bool valid;
-      long long yoff, rrow, r1pix;
-      int nimg, oh, ow;
-      if (p.flat) {
-        const long long pix = pix0 + rr;
-        valid = pix < p.total_pix;
-        nimg = (int)(pix / HWo);
-        const int rem = (int)(pix - (long long)nimg * HWo);
-        oh = rem / d.OW; ow = rem - oh * d.OW;
-        rrow = pix;
-      } else {
-        const int th = rr / p.TW, tw = rr - th * p.TW;
-        oh = oh0 + th; ow = ow0 + tw;
-        nimg = img;
-        valid = (rr < p.TH * p.TW) && oh < d.OH && ow < d.OW;
-        rrow = ((long long)img * d.OH + oh) * d.OW + ow;
+    int cg = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int n0 = nt * BN;
+      float sum[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+      for (int c = 0; c < n_chunks; ++c, ++cg) {
+        const int b = cg & 1;
+        mbar_wait(&acc_full[b], (cg >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * 2 * BN);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_main + c0, v);
+          if (p.terms == 3) {
+            uint32_t u[32];
+            tmem_ld32(t_main + BN + c0, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);   // fp32 RN adds
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
       }
-      if (!valid || !col_ok) continue;
-      yoff = nimg * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld;
-      r1pix = d.res_mode == TT_RES_UP2_NEAREST
-                  ? ((long long)nimg * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW
-                  : rrow;
-      const float4 t = *reinterpret_cast<const float4*>(&tile[rr * PITCH + cl]);
-      float o[4] = {t.x, t.y, t.z, t.w};
-      if (p.bias) {
-        bv = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)(nimg % d.bias_n_mod) * d.Cout : 0) + col));
-        o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+      // ---- this thread's row -> output / residual addresses (once per tile, 32-bit math where possible)
+      {
+        bool valid;
+        int nimg, oh, ow;
+        long long rrow;
+        if (p.flat) {
+          const long long pix = (long long)mt * BM + r;
+          valid = pix < p.total_pix;
+          nimg = (int)(pix / HWo);
+          const int rem = (int)(pix - (long long)nimg * HWo);
+          oh = rem / d.OW; ow = rem - oh * d.OW;
+          rrow = pix;
+        } else {
+          const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h;
+          nimg = mt / (p.tiles_w * p.tiles_h);
+          const int rh = r / p.TW, rw = r - rh * p.TW;
+          oh = th * p.TH + rh; ow = tw * p.TW + rw;
+          valid = (r < p.TH * p.TW) && oh < d.OH && ow < d.OW;
+          rrow = ((long long)nimg * d.OH + oh) * d.OW + ow;
+        }
+        row_y[r] = nimg * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld + d.y_coff;
+        row_r1[r] = (d.res_mode == TT_RES_UP2_NEAREST
+                         ? ((long long)nimg * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW
+                         : rrow) * d.res_ld + d.res_coff;
+        row_r2[r] = rrow * d.res2_ld + d.res2_coff;
+        row_flag[r] = (valid ? 1 : 0) | (nimg << 1);
       }
-      if (p.res) { const float4 u = *reinterpret_cast<const float4*>(p.res + r1pix * d.res_ld + d.res_coff + col); o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w; }
-      if (p.res2) { const float4 u = *reinterpret_cast<const float4*>(p.res2 + rrow * d.res2_ld + d.res2_coff + col); o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w; }
-      *reinterpret_cast<float4*>(p.y + yoff + d.y_coff + col) =
-          make_float4(tt_act(o[0], d.act), tt_act(o[1], d.act), tt_act(o[2], d.act), tt_act(o[3], d.act));
+      // ---- coalesced store in 32-column slabs: registers -> smem (transpose) -> 128-byte row segments
+      const int sub = lane >> 3, cl = (lane & 7) * 4;        // 8 lanes per row, 4 rows per warp instruction
+#pragma unroll
+      for (int sl = 0; sl < BN / 32; ++sl) {
+        __syncwarp();                                          // every row a warp reads below was written by its own lanes
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(&tile[r * PITCH + j]) =
+              make_float4(sum[sl * 32 + j], sum[sl * 32 + j + 1], sum[sl * 32 + j + 2], sum[sl * 32 + j + 3]);
+        __syncwarp();
+        const int col = n0 + sl * 32 + cl;
+        if (col < d.Cout) {
+          float4 acc4[8], ra[8], rb[8];
+          int fl[8];
+          long long yo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {                       // batch the loads of 8 row groups (memory-level parallelism)
+            const int rr = q * 32 + i * 4 + sub;
+            fl[i] = row_flag[rr];
+            yo[i] = row_y[rr];
+            acc4[i] = *reinterpret_cast<const float4*>(&tile[rr * PITCH + cl]);
+            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[i] = ra[i];
+            if (fl[i] & 1) {
+              if (p.res) ra[i] = *reinterpret_cast<const float4*>(p.res + row_r1[rr] + col);
+              if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + row_r2[rr] + col);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!(fl[i] & 1)) continue;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout : 0) + col));
+            const float4 o = make_float4(acc4[i].x + bv.x + ra[i].x + rb[i].x, acc4[i].y + bv.y + ra[i].y + rb[i].y,
+                                         acc4[i].z + bv.z + ra[i].z + rb[i].z, acc4[i].w + bv.w + ra[i].w + rb[i].w);
+            *reinterpret_cast<float4*>(p.y + yo[i] + col) =
+                make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
+          }
+        }
+      }
     }
   }
   tcgen05_fence_before();
@@ -457,14 +487,20 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     if (!encode_map(&mb_hi, w_tc, 3, dims, str, box)) return TT_ERR_CUDA;
     if (!encode_map(&mb_lo, w_tc + wplane, 3, dims, str, box)) return TT_ERR_CUDA;
   }
-  dim3 grid(grid_x, tt_cdiv(d->Cout, BN));
+  a.m_tiles = grid_x;
+  a.n_tiles = tt_cdiv(d->Cout, BN);
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const long long tiles = (long long)a.m_tiles * a.n_tiles;
+  dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));          // persistent: one CTA per SM
+  constexpr int EPI_BYTES = BM * 36 * 4 + BM * (3 * 8 + 4) + 256;      // slab + row tables + barriers
   if (BN == 128) {
-    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + 256;
+    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;
     if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
     conv_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
   } else {
-    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + 256;
+    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
     conv_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);

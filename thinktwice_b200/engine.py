@@ -170,8 +170,14 @@ class Engine:
             d.res_mode, d.res_ld = lib.RES_SAME, res.shape[1]
         d.taps, d.M = taps, cap
         d.impl = lib.IMPL_SIMT
+        if self.prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         lib.check(lib.load().tt_conv2d(C.byref(d), _p(feats), _p(pw.w), _p(pw.bias), _p(res), None, _p(nbr), _p(count),
                                        _p(out), None, _stream()), f'tt_conv2d[sparse {name}]')
+        if self.prof is not None:
+            ev1.record()
+            self.prof.append((f'sparse.{name}', 0.0, ev0, ev1))    # data-dependent work: algorithmic FLOPs not counted
         return out
 
     # ------------------------------------------------------------------ memory-bound ops
