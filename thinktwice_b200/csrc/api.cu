@@ -6,6 +6,7 @@
 
 static thread_local char g_err[512] = "";
 long long g_tt_launches = 0;
+int g_tt_debug = 0;   // diagnosis knobs for kernel micro-benchmarks (tools/conv_bench.py); 0 in normal operation
 
 void tt_set_error(const char* fmt, ...) {
   va_list ap;
@@ -25,6 +26,7 @@ extern "C" {
 int tt_version(void) { return 100; }
 const char* tt_last_error(void) { return g_err; }
 long long tt_launch_count(void) { return g_tt_launches; }
+void tt_debug_set(int flags) { g_tt_debug = flags; }
 
 int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
               const float* res2, const int* gather, const int* m_count, float* y, void* workspace, tt_stream_t stream) {

@@ -31,15 +31,23 @@ void tt_set_error(const char* fmt, ...);
 
 static inline int tt_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-TT_DEVICE float tt_act(float v, int act) {
+// Activations.  NONE / RELU are inlined; everything with a transcendental (erff, expf, log1pf are ~100 SASS
+// instructions each) lives in ONE out-of-line copy per translation unit: inlining it into fully unrolled GEMM
+// epilogues blew the tcgen05 kernel up to 392 KB of SASS and made its epilogue instruction-cache bound
+// (profiles/r1_summary_tc.md).
+static __device__ __noinline__ float tt_act_slow(float v, int act) {
   switch (act) {
-    case TT_ACT_RELU: return v > 0.f ? v : 0.f;
     case TT_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
     case TT_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     case TT_ACT_SOFTPLUS: return v > 20.f ? v : log1pf(expf(v));
     case TT_ACT_SOFTPLUS_CLAMP: return fmaxf(v > 20.f ? v : log1pf(expf(v)), 1e-3f);
     default: return v;
   }
+}
+TT_DEVICE float tt_act(float v, int act) {
+  if (act == TT_ACT_NONE) return v;
+  if (act == TT_ACT_RELU) return fmaxf(v, 0.f);
+  return tt_act_slow(v, act);
 }
 
 TT_DEVICE float warp_sum(float v) {

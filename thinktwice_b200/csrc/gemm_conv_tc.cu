@@ -23,6 +23,7 @@
 #include "common.cuh"
 
 extern long long g_tt_launches;
+extern int g_tt_debug;
 
 namespace {
 
@@ -118,6 +119,7 @@ struct TcArgs {
   int terms;             // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi only
   int chunk;             // K slabs accumulated inside TMEM before the epilogue folds them into fp32 registers
   int total_pix;         // N * OH * OW
+  int dbg;               // diagnosis knobs (tt_debug_set): 1 = no epilogue global traffic, 2 = no A loads, 4 = no MMAs
   int m_tiles, n_tiles;  // persistent tile walk: tile t -> (m tile t / n_tiles, n tile t % n_tiles)
 };
 
@@ -196,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================================================================== TMA producer
     if (lane == 0) {
       const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KS * 4;   // bytes one activation box delivers
-      const uint32_t tx = (p.terms == 3 ? 2 : 1) * (a_box + B_BYTES);
+      const uint32_t tx = (p.terms == 3 ? 2 : 1) * (((p.dbg & 2) ? 0u : a_box) + B_BYTES);
       int ig = 0;                                                               // ring position, continues across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;
@@ -216,10 +218,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int kh = tap / d.KW, kw = tap - kh * d.KW;
           mbar_expect_tx(&full[s], tx);
           const int cw = p.flat ? cw0 : cw0 + kw * d.dil, ch = p.flat ? 0 : ch0 + kh * d.dil;
-          tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
+          if (!(p.dbg & 2)) tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
           tma_load_3d(st + 2 * A_BYTES, &map_b_hi, &full[s], slab * KS, tap, n0);
           if (p.terms == 3) {
-            tma_load_4d(st + A_BYTES, &map_a_lo, &full[s], slab * KS, cw, ch, cn);
+            if (!(p.dbg & 2)) tma_load_4d(st + A_BYTES, &map_a_lo, &full[s], slab * KS, cw, ch, cn);
             tma_load_3d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, &full[s], slab * KS, tap, n0);
           }
         }
@@ -247,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
             for (int kk = 0; kk < KS / 8; ++kk) {            // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+              if (p.dbg & 4) break;
               const uint32_t off = kk * 32;
               const uint32_t acc = (first && kk == 0) ? 0u : 1u;
               umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
@@ -337,7 +340,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               make_float4(sum[sl * 32 + j], sum[sl * 32 + j + 1], sum[sl * 32 + j + 2], sum[sl * 32 + j + 3]);
         __syncwarp();
         const int col = n0 + sl * 32 + cl;
-        if (col < d.Cout) {
+        if (col < d.Cout && !(p.dbg & 1)) {
           float4 acc4[8], ra[8], rb[8];
           int fl[8];
           long long yo[8];
@@ -361,8 +364,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout : 0) + col));
             const float4 o = make_float4(acc4[i].x + bv.x + ra[i].x + rb[i].x, acc4[i].y + bv.y + ra[i].y + rb[i].y,
                                          acc4[i].z + bv.z + ra[i].z + rb[i].z, acc4[i].w + bv.w + ra[i].w + rb[i].w);
-            *reinterpret_cast<float4*>(p.y + yo[i] + col) =
-                make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
+            float* dst = p.y + ((p.dbg & 8) ? (long long)(threadIdx.x * 4) : yo[i] + col);   // dbg 8: all stores hit one hot 2 KB
+            if (!(p.dbg & 16) || o.x == 12345.678f)                                          // dbg 16: no store at all
+              *reinterpret_cast<float4*>(dst) =
+                  make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
           }
         }
       }
@@ -487,6 +492,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     if (!encode_map(&mb_hi, w_tc, 3, dims, str, box)) return TT_ERR_CUDA;
     if (!encode_map(&mb_lo, w_tc + wplane, 3, dims, str, box)) return TT_ERR_CUDA;
   }
+  a.dbg = g_tt_debug;
   a.m_tiles = grid_x;
   a.n_tiles = tt_cdiv(d->Cout, BN);
   static int num_sms = 0;
