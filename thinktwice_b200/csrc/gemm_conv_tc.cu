@@ -30,7 +30,7 @@ namespace {
 constexpr int BM = 128;          // UMMA M
 constexpr int KS = 32;           // floats per K slab (one 128-byte swizzle row)
 constexpr int STAGES = 3;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 TT_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,10 +159,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr int B_BYTES = BN * KS * 4;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr int TMEM_COLS = 4 * BN;                       // 2 (ping-pong) x {main, corr} x BN fp32 columns
-  constexpr int PITCH = 36;                               // epilogue slab: 128 rows x 32 columns (+4 pad: conflict-free)
+  constexpr int SLAB = 16;                                // epilogue slab: 16 columns of a warp's 32 rows
+  constexpr int PITCH = SLAB + 4;                         // +4 floats: conflict-free transposition
+  constexpr int HN = BN / 2;                              // columns owned by one epilogue warp (column half)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* tile = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);                  // [128][36]
-  long long* row_y = reinterpret_cast<long long*>(tile + BM * PITCH);                   // [128] output offset of row
+  float* tile_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);              // [8 warps][32 rows][PITCH]
+  long long* row_y = reinterpret_cast<long long*>(tile_all + 8 * 32 * PITCH);                   // [128] output offset of row
   long long* row_r1 = row_y + BM;                                                       // [128] residual-1 pixel
   long long* row_r2 = row_r1 + BM;                                                      // [128] residual-2 pixel (= GEMM row)
   int* row_flag = reinterpret_cast<int*>(row_r2 + BM);                                  // [128] valid | image << 1
@@ -182,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }   // 4 epilogue warps arrive
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }   // 8 epilogue warps arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -266,43 +268,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5 -> TMEM lane quarters)
+    // ===================================================================== epilogue (warps 2..9)
     const int q = warp & 3;                                // this warp may touch TMEM lanes [32q, 32q + 32)
+    const int half = (warp - 2) >> 2;                      // and owns columns [half * HN, half * HN + HN) of the tile
     const int r = q * 32 + lane;                           // accumulator row = pixel within the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
     const int HWo = d.OH * d.OW;
+    float* tile = tile_all + (warp - 2) * 32 * PITCH;      // warp-private transposition buffer [32 rows][PITCH]
     int cg = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-      const int n0 = nt * BN;
-      float sum[BN];
-#pragma unroll
-      for (int j = 0; j < BN; ++j) sum[j] = 0.f;
-      for (int c = 0; c < n_chunks; ++c, ++cg) {
-        const int b = cg & 1;
-        mbar_wait(&acc_full[b], (cg >> 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * 2 * BN);
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_main + c0, v);
-          if (p.terms == 3) {
-            uint32_t u[32];
-            tmem_ld32(t_main + BN + c0, u);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);   // fp32 RN adds
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-          }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
-      }
-      // ---- this thread's row -> output / residual addresses (once per tile, 32-bit math where possible)
+      const int n0 = nt * BN + half * HN;
+      // ---- this thread's row -> output / residual addresses (once per tile); prefetch the residual lines into L2
       {
         bool valid;
         int nimg, oh, ow;
@@ -322,34 +300,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           valid = (r < p.TH * p.TW) && oh < d.OH && ow < d.OW;
           rrow = ((long long)nimg * d.OH + oh) * d.OW + ow;
         }
-        row_y[r] = nimg * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld + d.y_coff;
-        row_r1[r] = (d.res_mode == TT_RES_UP2_NEAREST
-                         ? ((long long)nimg * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW
-                         : rrow) * d.res_ld + d.res_coff;
-        row_r2[r] = rrow * d.res2_ld + d.res2_coff;
-        row_flag[r] = (valid ? 1 : 0) | (nimg << 1);
+        const long long r1 = (d.res_mode == TT_RES_UP2_NEAREST
+                                  ? ((long long)nimg * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW
+                                  : rrow) * d.res_ld + d.res_coff;
+        const long long r2 = rrow * d.res2_ld + d.res2_coff;
+        if (half == 0) {                                    // both column halves would write identical values
+          row_y[r] = nimg * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld + d.y_coff;
+          row_r1[r] = r1;
+          row_r2[r] = r2;
+          row_flag[r] = (valid ? 1 : 0) | (nimg << 1);
+        }
+        if (valid && n0 < d.Cout) {
+          if (p.res) {
+#pragma unroll
+            for (int j = 0; j < HN; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + r1 + n0 + j));
+          }
+          if (p.res2) {
+#pragma unroll
+            for (int j = 0; j < HN; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res2 + r2 + n0 + j));
+          }
+        }
       }
-      // ---- coalesced store in 32-column slabs: registers -> smem (transpose) -> 128-byte row segments
-      const int sub = lane >> 3, cl = (lane & 7) * 4;        // 8 lanes per row, 4 rows per warp instruction
+      float sum[HN];
 #pragma unroll
-      for (int sl = 0; sl < BN / 32; ++sl) {
-        __syncwarp();                                          // every row a warp reads below was written by its own lanes
+      for (int j = 0; j < HN; ++j) sum[j] = 0.f;
+      for (int c = 0; c < n_chunks; ++c, ++cg) {
+        const int b = cg & 1;
+        mbar_wait(&acc_full[b], (cg >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * 2 * BN + half * HN);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(&tile[r * PITCH + j]) =
-              make_float4(sum[sl * 32 + j], sum[sl * 32 + j + 1], sum[sl * 32 + j + 2], sum[sl * 32 + j + 3]);
+        for (int c0 = 0; c0 < HN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_main + c0, v);
+          if (p.terms == 3) {
+            uint32_t u[32];
+            tmem_ld32(t_main + BN + c0, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);   // fp32 RN adds
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tcgen05_fence_before();
         __syncwarp();
-        const int col = n0 + sl * 32 + cl;
-        if (col < d.Cout && !(p.dbg & 1)) {
-          float4 acc4[8], ra[8], rb[8];
-          int fl[8];
-          long long yo[8];
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");         // row tables written by the half-0 warps are visible
+      // ---- coalesced store in 16-column slabs: registers -> smem (transpose) -> 64-byte row segments, 8 rows / instr
+      const int sub = lane >> 2, cl = (lane & 3) * 4;        // 4 lanes per row, 8 rows per warp instruction
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {                       // batch the loads of 8 row groups (memory-level parallelism)
-            const int rr = q * 32 + i * 4 + sub;
+      for (int sl = 0; sl < HN / SLAB; ++sl) {
+        __syncwarp();                                          // the previous slab has been read back by this warp
+#pragma unroll
+        for (int j = 0; j < SLAB; j += 4)
+          *reinterpret_cast<float4*>(&tile[lane * PITCH + j]) =
+              make_float4(sum[sl * SLAB + j], sum[sl * SLAB + j + 1], sum[sl * SLAB + j + 2], sum[sl * SLAB + j + 3]);
+        __syncwarp();
+        const int col = n0 + sl * SLAB + cl;
+        if (col < d.Cout && !(p.dbg & 1)) {
+          float4 acc4[4], ra[4], rb[4];
+          int fl[4];
+          long long yo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                       // batch the loads of 4 x 8 rows (memory-level parallelism)
+            const int lr = i * 8 + sub, rr = q * 32 + lr;
             fl[i] = row_flag[rr];
             yo[i] = row_y[rr];
-            acc4[i] = *reinterpret_cast<const float4*>(&tile[rr * PITCH + cl]);
+            acc4[i] = *reinterpret_cast<const float4*>(&tile[lr * PITCH + cl]);
             ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             rb[i] = ra[i];
             if (fl[i] & 1) {
@@ -358,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             if (!(fl[i] & 1)) continue;
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout : 0) + col));
@@ -371,6 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");         // everyone is done with the row tables before the next tile
     }
   }
   tcgen05_fence_before();
@@ -499,7 +519,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   const long long tiles = (long long)a.m_tiles * a.n_tiles;
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));          // persistent: one CTA per SM
-  constexpr int EPI_BYTES = BM * 36 * 4 + BM * (3 * 8 + 4) + 256;      // slab + row tables + barriers
+  constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 256;  // 8 warp-private slabs + row tables + barriers
   if (BN == 128) {
     constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;

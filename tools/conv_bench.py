@@ -44,7 +44,7 @@ def main():
         gf = 2.0 * N * OH * OW * Cin * k * k * Cout / 1e9
         mb = (N * H * W * Cin + N * OH * OW * Cout * (2 if use_res else 1)) * 4 / 1e6
         line = f'{name:36s} {gf:7.1f} GF {mb:6.0f} MB(min)'
-        for impl, tag in ((1, 'simt'), (2, 'tf32'), (3, '3xtf32')):
+        for impl, tag in [(int(i), {1: 'simt', 2: 'tf32', 3: '3xtf32'}[int(i)]) for i in os.environ.get('IMPLS', '1,2,3').split(',')]:
             eng = Engine('cuda:0', impl=impl); eng.tc_min_rows = 1
             pw = Packer({'c.weight': w}, torch.device('cuda:0'), tc_mode=impl if impl > 1 else 0).conv('c')
             for dbg in (dbg_list if impl > 1 else [0]):
