@@ -23,8 +23,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = 'frames/sec full encoder+decoder fwd (thinktwice.py: 4-cam x 2-sweep 448x896 + LiDAR, 21x21 BEV, K=5)'
-WORKLOAD = 'configs[1]: thinktwice.py, batch 1 per GPU'
+METRIC = json.load(open(os.path.join(ROOT, 'BASELINE.json')))['metric'] if os.path.exists(os.path.join(ROOT, 'BASELINE.json')) else \
+    'frames/sec full encoder+decoder fwd (4-cam+LiDAR, 200\u00d7200 BEV) at 1/2/4/8 B200'
+WORKLOAD = ('configs[1]: thinktwice.py config, 4 cams x 2 sweeps 448x896 + 40k-point LiDAR, K=5 decoder, batch 1 per GPU '
+            '(the config file yields a 21x21 camera BEV / 84x84 LiDAR BEV, not 200x200: SURVEY.md fact 3)')
 # dense MACs per frame (camera 1127.7 G + LiDAR dense 13.7 G + fusion 4.25 G + decoder 63.3 G)
 ALGO_FLOPS_PER_FRAME = 2 * 1.209e12
 
@@ -171,13 +173,14 @@ def main():
     for k in ('img', 'points', 'speed', 'target_point', 'target_command'):
         host[k] = host[k].pin_memory()
     resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
-    gathered = [torch.empty(B, 6, 4, 2, device=dev) for _ in range(world)] if world > 1 else None
+    from thinktwice_b200.parallel import gather_waypoints
+    gathered = torch.empty(world * B, 6, 4, 2, device=dev) if world > 1 else None
 
     def step(batch):
         pred = model.forward_inference(batch)
         wp = pred['pred_wp']
         if world > 1:                                            # the path's single collective: gather of the waypoints
-            dist.all_gather(gathered, wp.contiguous())
+            return gather_waypoints(wp, world, out=gathered)
         return wp
 
     def timed(batch, steps, read_back):

@@ -36,6 +36,8 @@ int tt_version(void);
 const char* tt_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long tt_launch_count(void);
+/* diagnosis knobs for kernel micro-benchmarks (tools/conv_bench.py); 0 in normal operation */
+void tt_debug_set(int flags);
 
 /* ------------------------------------------------------------------------------------------
  * (1) voxel pooling — drop-in for the reference's only in-tree native op.

@@ -1,0 +1,72 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tt_b200.h declares (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'tt_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(tt_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from thinktwice_b200 import lib
+    if not os.path.exists(lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    L = C.CDLL(lib.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(syms) <= set(lib.EXPORTS) | {'tt_debug_set'} or not (set(syms) - set(lib.EXPORTS) - {'tt_debug_set'})
+    L.tt_version.restype = C.c_int
+    assert L.tt_version() >= 100
+    L.tt_last_error.restype = C.c_char_p
+    assert isinstance(L.tt_last_error(), bytes)
+
+
+def test_product_fails_loudly_without_cuda():
+    import pytest
+    import torch
+    from thinktwice_b200 import lib
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.registry import build_model
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    m = build_model(Config.fromfile(PLUMBING_CONFIG).model)
+    with pytest.raises(lib.TTError):
+        m.prepare('cpu')
+    from thinktwice_b200.ops.voxel_pooling import voxel_pooling
+    with pytest.raises(lib.TTError):
+        voxel_pooling(torch.zeros(1, 4, 3, dtype=torch.int32), torch.zeros(1, 4, 8), torch.tensor([2, 2, 1]))
+
+
+def test_config_model_section_equals_reference_when_present():
+    from thinktwice_b200.config import Config, DEFAULT_CONFIG
+    ref_path = '/root/reference/open_loop_training/configs/thinktwice.py'
+    ours = Config.fromfile(DEFAULT_CONFIG)
+    assert ours.model.decoder.config.pred_len == 4 and ours.model.img_encoder.final_dim == (448, 896)
+    if not os.path.exists(ref_path):
+        return
+    ref = Config.fromfile(ref_path)
+
+    def norm(x):
+        if isinstance(x, dict):
+            return {k: norm(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [norm(v) for v in x]
+        return x
+
+    def diff(a, b, path=''):
+        out = []
+        if isinstance(a, dict):
+            for k in a:                                            # every key we carry must equal the reference's
+                out += diff(a[k], b.get(k, '<missing>'), path + '/' + k) if isinstance(b, dict) else [path]
+        elif a != b:
+            out.append((path, a, b))
+        return out
+    assert not diff(norm(ours.model), norm(ref.model))

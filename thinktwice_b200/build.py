@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
             print(' '.join(cmd)); print(out)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart', '-lcuda']
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs
     subprocess.check_call(cmd)
     with open(stamp, 'w') as f:
         f.write(dig)

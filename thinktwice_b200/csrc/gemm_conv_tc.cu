@@ -407,13 +407,25 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
   // spatial_stride > 1 (strided convolution): TMA traverses W and H with that element stride, loading
   // ceil(box / stride) pixels per dimension — the strided im2col gather is done by the copy engine.
   cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
-  CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  // libcuda is not linked (the library must load on machines without a driver): resolve the encoder through the runtime
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      tt_set_error("tt_conv2d(tc): cuTensorMapEncodeTiled is not available from this driver");
+      return false;
+    }
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    const char* s = nullptr;
-    cuGetErrorString(r, &s);
-    tt_set_error("tt_conv2d(tc): cuTensorMapEncodeTiled failed: %s", s ? s : "?");
+    tt_set_error("tt_conv2d(tc): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return false;
   }
   return true;
