@@ -188,10 +188,24 @@ typedef struct {
   int table_size;                /* power of two >= 2 * max(cap_in, cap_out) */
 } tt_rulebook_desc;
 size_t tt_rulebook_workspace_bytes(const tt_rulebook_desc* d);
-/* Builds out_coords/out_count (copied from the input for subm) and nbr [cap_out][kvol]
- * (input row per tap or -1). */
+/* Builds out_coords/out_count (copied from the input for subm) and, whichever is non-NULL:
+ *   nbr [cap_out][kvol]                      : input row per (output row, tap) or -1 (output-stationary gather), and/or
+ *   pairs_in / pairs_out [kvol][cap_out], pair_count [kvol] : tap-major (input row, output row) lists. */
 int tt_sparse_rulebook(const tt_rulebook_desc* d, const int* in_coords, const int* in_count, int* out_coords,
-                       int* out_count, int* nbr, void* workspace, tt_stream_t stream);
+                       int* out_count, int* nbr, int* pairs_in, int* pairs_out, int* pair_count, void* workspace,
+                       tt_stream_t stream);
+/* Tap-major sparse convolution: out[o] = act(sum_tap w[tap] . in[i] + bias + res[o]) over the rulebook's pairs; one
+ * gather-GEMM per tap (output rows of a tap are distinct, taps are stream-ordered: no atomics, fixed summation order).
+ * w: [kvol][Cin][Cout] fp32 (BatchNorm folded), res: optional [cap_out][res_ld] (SparseBasicBlock identity). */
+typedef struct {
+  int Cin, Cout, kvol;
+  int in_ld, out_ld, res_ld;
+  int cap_out, pair_cap;         /* pair lists are [kvol][pair_cap] */
+  int act;
+} tt_sparse_conv_desc;
+int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_in, const float* w, const float* bias,
+                   const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,
+                   const int* out_count, float* feats_out, tt_stream_t stream);
 /* dense()[N][C][D][H][W].view(N, C*D, H, W) (lidarnet.py:53-56) written channels-last, channel = c*D + z,
  * with the framework's anti-transpose (framework:246) folded in when asked; `dense` must be zero-filled. */
 int tt_sparse_to_bev(const float* feats, const int* coords, const int* count, int cap, int C, int D, int H, int W,

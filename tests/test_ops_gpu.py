@@ -345,13 +345,17 @@ def test_sparse_conv_layers_match_oracle(eng):
         oc = torch.zeros(cap_out, 4, dtype=torch.int32, device='cuda'); ocount = torch.zeros(1, dtype=torch.int32, device='cuda')
         kvol = k[0] * k[1] * k[2]
         nbr = torch.zeros(cap_out, kvol, dtype=torch.int32, device='cuda')
-        lib.call('tt_sparse_rulebook', C.byref(d), _p(ic), _p(icount), _p(oc), _p(ocount), _p(nbr), _p(ws))
+        pin, pout = (torch.zeros(kvol, cap_out, dtype=torch.int32, device='cuda') for _ in range(2))
+        pcount = torch.zeros(kvol, dtype=torch.int32, device='cuda')
+        lib.call('tt_sparse_rulebook', C.byref(d), _p(ic), _p(icount), _p(oc), _p(ocount), _p(nbr), _p(pin), _p(pout), _p(pcount), _p(ws))
+        assert int(pcount.sum()) == int((nbr[:int(ocount.item())] >= 0).sum())               # both rulebook forms agree
         w = conv.weight.detach()
         from thinktwice_b200.engine import PackedConv
         pw = PackedConv(w.reshape(Cout, kvol, Cin).permute(1, 2, 0).reshape(kvol * Cin, Cout).contiguous().cuda(), None, Cin, Cout)
         fin = torch.zeros(cap_in, Cin, device='cuda'); fin[:n] = feats.cuda()
         out = torch.zeros(cap_out, Cout, device='cuda')
-        eng.sparse_conv(fin, pw, nbr, ocount, cap_out, kvol, out)
+        rule = dict(kvol=kvol, cap=cap_out, pairs_in=pin, pairs_out=pout, pair_count=pcount, count=ocount)
+        eng.sparse_conv(fin, pw, rule, out)
         m = int(ocount.item())
         D, H, W = out_shape
         dense = torch.zeros(B, H, W, Cout * D, device='cuda')

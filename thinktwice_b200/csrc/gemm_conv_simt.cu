@@ -9,7 +9,11 @@
 // Tiling: BMxBNx16 per CTA, 256 threads, TMxTN register tile split into 4x4 quadrants so that
 // shared-memory reads are conflict-free 128-bit loads (A broadcast, B contiguous), global->register
 // prefetch of the next K slab overlapped with the FFMA block, double-buffered shared memory.
+#include <string.h>
+
 #include "common.cuh"
+
+extern long long g_tt_launches;
 
 namespace {
 
@@ -26,6 +30,8 @@ struct ConvArgs {
   int M, Cin_g, Cout_g, Kg, taps;
   int splits, k_per_split;   // split-K (small-M / large-K layers): partial sums go to `partial`, reduced by a 2nd kernel
   float* partial;            // [splits][M][Cout]
+  const int* out_index;      // gather mode: output row of GEMM row m (tap-major sparse conv pairs); NULL = m
+  int accumulate;            // gather mode: y[row] += result (rows of one launch are distinct)
 };
 
 constexpr int BK = 16;
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
     long long yoff, rpix = row, r1pix = row;
     int n = 0;
     if (p.gather) {
-      yoff = (long long)row * d.y_ld;
+      yoff = (long long)(p.out_index ? p.out_index[row] : row) * d.y_ld;
     } else {
       const int ow = row % d.OW;
       const int t = row / d.OW;
@@ -249,6 +255,13 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = acc[i][q * 4 + j];
+      if (p.accumulate) {                                   // tap-major sparse conv: read-modify-write of a row this launch owns
+        if (vec_out) { const float4 t = *reinterpret_cast<const float4*>(yrow + col); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (col + j < p.Cout_g) v[j] += yrow[col + j];
+        }
+      }
       if (vec_out) {
         if (bs) { const float4 t = __ldg(reinterpret_cast<const float4*>(bs + col)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
         if (r1) { const float4 t = *reinterpret_cast<const float4*>(r1 + col); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
@@ -312,8 +325,6 @@ void launch_cfg(const ConvArgs& a, bool veca, bool vecb, cudaStream_t st) {
 
 }  // namespace
 
-extern long long g_tt_launches;
-
 // split-K plan shared by the launcher and tt_conv2d_workspace_bytes
 int tt_simt_splits(const tt_conv_desc* d, int has_gather) {
   const int taps = has_gather ? d->taps : d->KH * d->KW;
@@ -346,6 +357,8 @@ int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const 
   a.splits = workspace ? tt_simt_splits(d, gather != nullptr) : 1;
   a.k_per_split = a.splits > 1 ? tt_cdiv(tt_cdiv(a.Kg, a.splits), BK) * BK : a.Kg;
   a.partial = static_cast<float*>(workspace);
+  a.out_index = nullptr;
+  a.accumulate = 0;
   const bool veca = (a.Cin_g % 4 == 0) && (d->x_ld % 4 == 0) && (d->x_coff % 4 == 0) && (d->x_nstride % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const bool vecb = (a.Cout_g % 4 == 0) && (d->Cout % 4 == 0) && (d->y_nstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
@@ -370,5 +383,70 @@ int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const 
   else launch_cfg<64, 64, 4, 4>(a, veca, vecb, st);
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_conv2d(simt)");
+  return TT_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tap-major sparse convolution (spconv SubMConv3d / SparseConv3d): the rulebook lists, per kernel tap, the (input row,
+// output row) pairs that exist.  One gather-GEMM launch per tap over just those pairs — instead of a 27-tap dense
+// gather where ~3 taps are populated — accumulating into the output rows (distinct within a tap, taps are stream-
+// ordered, so no atomics and a fixed summation order).  out = act(sum_taps W_tap . in[pair] + bias + res).
+namespace {
+__global__ void sparse_rows_init_kernel(float* __restrict__ y, int ld, const float* __restrict__ bias, int C,
+                                        const int* __restrict__ count, int cap) {
+  const int n = min(*count, cap);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * C; i += (long long)gridDim.x * blockDim.x)
+    y[(i / C) * ld + (i % C)] = bias ? __ldg(bias + (i % C)) : 0.f;
+}
+__global__ void sparse_rows_finish_kernel(float* __restrict__ y, int ld, const float* __restrict__ res, int res_ld, int C,
+                                          const int* __restrict__ count, int cap, int act) {
+  const int n = min(*count, cap);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * C; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = i % C;
+    float v = y[r * ld + c];
+    if (res) v += res[r * res_ld + c];
+    y[r * ld + c] = tt_act(v, act);
+  }
+}
+}  // namespace
+
+extern "C" int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_in, const float* w, const float* bias,
+                              const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,
+                              const int* out_count, float* feats_out, tt_stream_t stream) {
+  TT_REQUIRE(d && feats_in && w && pairs_in && pairs_out && pair_count && out_count && feats_out, "tt_sparse_conv", "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->cap_out <= 0) return TT_OK;
+  const long long tot = (long long)d->cap_out * d->Cout;
+  const int nb = (int)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256);
+  sparse_rows_init_kernel<<<nb, 256, 0, st>>>(feats_out, d->out_ld, bias, d->Cout, out_count, d->cap_out);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_sparse_conv(init)");
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d.N = a.d.H = a.d.W = a.d.OH = a.d.OW = a.d.yH = a.d.yW = 1;
+  a.d.KH = a.d.KW = a.d.stride = a.d.dil = a.d.groups = 1;
+  a.d.oy_mul = a.d.ox_mul = 1;
+  a.d.Cin = d->Cin; a.d.x_ld = d->in_ld; a.d.Cout = d->Cout; a.d.y_ld = d->out_ld;
+  a.d.act = TT_ACT_NONE;
+  a.x = feats_in; a.y = feats_out;
+  a.M = d->pair_cap; a.Cin_g = d->Cin; a.Cout_g = d->Cout; a.Kg = d->Cin; a.taps = 1;
+  a.splits = 1; a.k_per_split = a.Kg; a.accumulate = 1;
+  const bool veca = (d->Cin % 4 == 0) && (d->in_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats_in) & 15) == 0);
+  const bool vecb = (d->Cout % 4 == 0) && (d->out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(feats_out) & 15) == 0);
+  for (int tap = 0; tap < d->kvol; ++tap) {
+    a.w = w + (long long)tap * d->Cin * d->Cout;
+    a.gather = pairs_in + (long long)tap * d->pair_cap;
+    a.out_index = pairs_out + (long long)tap * d->pair_cap;
+    a.m_count = pair_count + tap;
+    launch_cfg<64, 64, 4, 4>(a, veca, vecb, st);
+    ++g_tt_launches;
+  }
+  TT_CHECK_LAUNCH("tt_sparse_conv(taps)");
+  sparse_rows_finish_kernel<<<nb, 256, 0, st>>>(feats_out, d->out_ld, res, d->res_ld, d->Cout, out_count, d->cap_out, d->act);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_sparse_conv(finish)");
   return TT_OK;
 }

@@ -143,7 +143,8 @@ __global__ void rb_gen_out_kernel(const tt_rulebook_desc d, const int* __restric
 }
 
 __global__ void rb_nbr_kernel(const tt_rulebook_desc d, const int* __restrict__ out_coords, const int* __restrict__ out_count,
-                              const u64* __restrict__ keys, const int* __restrict__ vals, int mask, int* __restrict__ nbr) {
+                              const u64* __restrict__ keys, const int* __restrict__ vals, int mask, int* __restrict__ nbr,
+                              int* __restrict__ pairs_in, int* __restrict__ pairs_out, int* pair_count) {
   const int kvol = d.k[0] * d.k[1] * d.k[2];
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int n = min(*out_count, d.cap_out);
@@ -162,7 +163,12 @@ __global__ void rb_nbr_kernel(const tt_rulebook_desc d, const int* __restrict__ 
     const int s = table_find(keys, mask, site_key(out_coords[o * 4], src[0], src[1], src[2], d.in_shape));
     if (s >= 0) r = vals[s];
   }
-  nbr[idx] = r;
+  if (nbr) nbr[idx] = r;
+  if (r >= 0 && pairs_in) {                                  // tap-major pair lists (order inside a tap is irrelevant)
+    const int pos = atomicAdd(&pair_count[tap], 1);
+    pairs_in[(long long)tap * d.cap_out + pos] = r;
+    pairs_out[(long long)tap * d.cap_out + pos] = o;
+  }
 }
 
 __global__ void clamp_count_kernel(int* count, int cap) { if (*count > cap) *count = cap; }
@@ -228,8 +234,10 @@ size_t tt_rulebook_workspace_bytes(const tt_rulebook_desc* d) {
 }
 
 int tt_sparse_rulebook(const tt_rulebook_desc* d, const int* in_coords, const int* in_count, int* out_coords,
-                       int* out_count, int* nbr, void* workspace, tt_stream_t stream) {
-  TT_REQUIRE(d && in_coords && in_count && out_coords && out_count && nbr && workspace, "tt_sparse_rulebook", "null argument");
+                       int* out_count, int* nbr, int* pairs_in, int* pairs_out, int* pair_count, void* workspace,
+                       tt_stream_t stream) {
+  TT_REQUIRE(d && in_coords && in_count && out_coords && out_count && workspace, "tt_sparse_rulebook", "null argument");
+  TT_REQUIRE(nbr || (pairs_in && pairs_out && pair_count), "tt_sparse_rulebook", "need nbr and/or the pair lists");
   const int T = d->table_size;
   TT_REQUIRE(T >= 1024 && (T & (T - 1)) == 0 && T >= 2 * d->cap_in && T >= 2 * d->cap_out, "tt_sparse_rulebook",
              "table_size must be a power of two >= 2*cap");
@@ -258,7 +266,9 @@ int tt_sparse_rulebook(const tt_rulebook_desc* d, const int* in_coords, const in
     clamp_count_kernel<<<1, 1, 0, st>>>(out_count, d->cap_out);
     TT_LAUNCHED("tt_sparse_rulebook(clamp)");
   }
-  rb_nbr_kernel<<<tt_cdiv((long long)d->cap_out * kvol, 256), 256, 0, st>>>(*d, out_coords, out_count, keys, vals, T - 1, nbr);
+  if (pair_count && cudaMemsetAsync(pair_count, 0, (size_t)kvol * 4, st) != cudaSuccess) { tt_set_error("tt_sparse_rulebook: memset failed"); return TT_ERR_CUDA; }
+  rb_nbr_kernel<<<tt_cdiv((long long)d->cap_out * kvol, 256), 256, 0, st>>>(*d, out_coords, out_count, keys, vals, T - 1, nbr,
+                                                                            pairs_in, pairs_out, pair_count);
   TT_LAUNCHED("tt_sparse_rulebook(nbr)");
   return TT_OK;
 }

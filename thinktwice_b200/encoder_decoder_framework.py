@@ -74,6 +74,8 @@ class EncoderDecoder(nn.Module):
     def prepare(self, device='cuda:0', impl=lib.IMPL_AUTO):
         dev = torch.device(device)
         lib.require_cuda(dev)
+        if impl == lib.IMPL_AUTO:
+            impl = lib.IMPL_3XTF32                                  # default engine: tcgen05 3xTF32 (fp32-class)
         self.eng = e = Engine(dev, impl)
         pk = Packer(self.params.state_dict(), dev, tc_mode=impl if impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) else 0)
         self.img_encoder.prepare(pk, e)

@@ -158,23 +158,18 @@ class Engine:
             out = out.as_rows()
         return self.conv(xr, pw, out=out, name=name, act=act, res=res.as_rows() if res is not None else None)
 
-    def sparse_conv(self, feats, pw, nbr, count, cap, taps, out, act=0, res=None, name=None):
-        """gather-mode GEMM: feats [cap_in][Cin] tensor, nbr [cap][taps] int32, count device int, out [cap][Cout]."""
-        d = ConvDesc()
-        d.N, d.H, d.W, d.Cin, d.x_ld, d.x_coff = 1, 1, 1, pw.Cin, feats.shape[1], 0
-        d.Cout, d.KH, d.KW, d.stride, d.pad, d.dil, d.groups = pw.Cout, 1, 1, 1, 0, 1, 1
-        d.OH, d.OW, d.y_ld, d.y_coff, d.yH, d.yW = 1, 1, out.shape[1], 0, 1, 1
-        d.oy_mul, d.oy_add, d.ox_mul, d.ox_add = 1, 0, 1, 0
-        d.act = act
-        if res is not None:
-            d.res_mode, d.res_ld = lib.RES_SAME, res.shape[1]
-        d.taps, d.M = taps, cap
-        d.impl = lib.IMPL_SIMT
+    def sparse_conv(self, feats, pw, rule, out, act=0, res=None, name=None):
+        """tap-major sparse conv over a rulebook `rule` (dict from LidarNet._rulebook): feats [cap_in][Cin] -> out [cap_out][Cout]."""
+        d = lib.SparseConvDesc()
+        d.Cin, d.Cout, d.kvol = pw.Cin, pw.Cout, rule['kvol']
+        d.in_ld, d.out_ld, d.res_ld = feats.shape[1], out.shape[1], (res.shape[1] if res is not None else 0)
+        d.cap_out, d.pair_cap, d.act = rule['cap'], rule['cap'], act
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        lib.check(lib.load().tt_conv2d(C.byref(d), _p(feats), _p(pw.w), _p(pw.bias), _p(res), None, _p(nbr), _p(count),
-                                       _p(out), None, _stream()), f'tt_conv2d[sparse {name}]')
+        lib.check(lib.load().tt_sparse_conv(C.byref(d), _p(feats), _p(pw.w), _p(pw.bias), _p(res), _p(rule['pairs_in']),
+                                            _p(rule['pairs_out']), _p(rule['pair_count']), _p(rule['count']), _p(out),
+                                            _stream()), f'tt_sparse_conv[{name}]')
         if self.prof is not None:
             ev1.record()
             self.prof.append((f'sparse.{name}', 0.0, ev0, ev1))    # data-dependent work: algorithmic FLOPs not counted

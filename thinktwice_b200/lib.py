@@ -48,6 +48,10 @@ class RulebookDesc(C.Structure):
                 ('table_size', C.c_int)]
 
 
+class SparseConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('Cin', 'Cout', 'kvol', 'in_ld', 'out_ld', 'res_ld', 'cap_out', 'pair_cap', 'act')]
+
+
 class LookDesc(C.Structure):
     _fields_ = [('B', C.c_int), ('num_cams', C.c_int), ('num_query', C.c_int), ('T', C.c_int),
                 ('img_w', C.c_float), ('img_h', C.c_float), ('levels', C.c_int),
@@ -87,7 +91,7 @@ EXPORTS = [
     'tt_maxpool3x3s2', 'tt_upsample2x_bilinear_ac', 'tt_global_avgpool', 'tt_broadcast_rows', 'tt_se_gate', 'tt_se_pool',
     'tt_se_apply', 'tt_anti_transpose', 'tt_copy2d', 'tt_layernorm', 'tt_eltwise', 'tt_fill', 'tt_dcn_im2col',
     'tt_voxelize_workspace_bytes', 'tt_voxelize_mean', 'tt_rulebook_workspace_bytes', 'tt_sparse_rulebook',
-    'tt_sparse_to_bev', 'tt_look_project', 'tt_look_rebatch', 'tt_msda_forward', 'tt_look_reduce', 'tt_gru_input',
+    'tt_sparse_conv', 'tt_sparse_to_bev', 'tt_look_project', 'tt_look_rebatch', 'tt_msda_forward', 'tt_look_reduce', 'tt_gru_input',
 ]
 
 

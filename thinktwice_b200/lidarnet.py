@@ -97,13 +97,13 @@ class LidarNet:
         d.table_size = _pow2(2 * max(cap_in, cap_out))
         kvol = k[0] * k[1] * k[2]
         ws = e.buf('sp.ws', (lib.load().tt_rulebook_workspace_bytes(C.byref(d)),), dtype=torch.uint8)
-        if subm:
-            out_coords, out_count = e.buf(f'sp.{tag}.coords', (cap_out, 4), torch.int32), e.buf(f'sp.{tag}.count', (1,), torch.int32)
-        else:
-            out_coords, out_count = e.buf(f'sp.{tag}.coords', (cap_out, 4), torch.int32), e.buf(f'sp.{tag}.count', (1,), torch.int32)
-        nbr = e.buf(f'sp.{tag}.nbr', (cap_out, kvol), torch.int32)
-        lib.call('tt_sparse_rulebook', C.byref(d), _p(in_coords), _p(in_count), _p(out_coords), _p(out_count), _p(nbr), _p(ws))
-        return out_coords, out_count, cap_out, out_shape, nbr, kvol
+        out_coords, out_count = e.buf(f'sp.{tag}.coords', (cap_out, 4), torch.int32), e.buf(f'sp.{tag}.count', (1,), torch.int32)
+        pin, pout = e.buf(f'sp.{tag}.pin', (kvol, cap_out), torch.int32), e.buf(f'sp.{tag}.pout', (kvol, cap_out), torch.int32)
+        pcount = e.buf(f'sp.{tag}.pcount', (kvol,), torch.int32)
+        lib.call('tt_sparse_rulebook', C.byref(d), _p(in_coords), _p(in_count), _p(out_coords), _p(out_count), None, _p(pin), _p(pout),
+                 _p(pcount), _p(ws))
+        return dict(coords=out_coords, count=out_count, cap=cap_out, shape=out_shape, kvol=kvol, pairs_in=pin, pairs_out=pout,
+                    pair_count=pcount)
 
     def forward(self, pts):
         """pts (B, P, 5) fp32 on the device -> [FMap (B, 84, 84, 512)] already in the Roach BEV orientation
@@ -129,24 +129,23 @@ class LidarNet:
 
         shape = self.me.sparse_shape
         # conv_input (SubM 5 -> 16); all SubM convs of one resolution share one rulebook (spconv indice_key)
-        coords, count, cap, shape, nbr, kvol = self._rulebook('l0', B, coords, count, cap, shape, self.k_in, (1, 1, 1), (1, 1, 1), True)
-        x = e.sparse_conv(feats, self.w_in, nbr, count, cap, kvol, e.buf('sp.l0.x', (cap, self.w_in.Cout)), act=ACT_RELU, name='conv_input')
+        rb = self._rulebook('l0', B, coords, count, cap, shape, self.k_in, (1, 1, 1), (1, 1, 1), True)
+        x = e.sparse_conv(feats, self.w_in, rb, e.buf('sp.l0.x', (rb['cap'], self.w_in.Cout)), act=ACT_RELU, name='conv_input')
         for i, st in enumerate(self.stages):
             for j, layer in enumerate(st):
                 if layer[0] == 'block':
                     _, w1, w2 = layer
-                    t = e.sparse_conv(x, w1, nbr, count, cap, kvol, e.buf(f'sp.l{i}.t', (cap, w1.Cout)), act=ACT_RELU, name=f'{i}.{j}.conv1')
-                    x = e.sparse_conv(t, w2, nbr, count, cap, kvol, e.buf(f'sp.l{i}.o{j % 2}', (cap, w2.Cout)), act=ACT_RELU, res=x,
-                                      name=f'{i}.{j}.conv2')
+                    t = e.sparse_conv(x, w1, rb, e.buf(f'sp.l{i}.t', (rb['cap'], w1.Cout)), act=ACT_RELU, name=f'{i}.{j}.conv1')
+                    x = e.sparse_conv(t, w2, rb, e.buf(f'sp.l{i}.o{j % 2}', (rb['cap'], w2.Cout)), act=ACT_RELU, res=x, name=f'{i}.{j}.conv2')
                 else:
                     _, wc, k, s, p = layer
-                    coords2, count2, cap2, shape2, nbr2, kv2 = self._rulebook(f'd{i}', B, coords, count, cap, shape, k, s, p, False)
-                    x = e.sparse_conv(x, wc, nbr2, count2, cap2, kv2, e.buf(f'sp.l{i + 1}.x', (cap2, wc.Cout)), act=ACT_RELU, name=f'{i}.{j}.down')
-                    coords, count, cap, shape = coords2, count2, cap2, shape2
+                    rd = self._rulebook(f'd{i}', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], k, s, p, False)
+                    x = e.sparse_conv(x, wc, rd, e.buf(f'sp.l{i + 1}.x', (rd['cap'], wc.Cout)), act=ACT_RELU, name=f'{i}.{j}.down')
                     # rulebook of the SubM convs at the new resolution
-                    coords, count, cap, shape, nbr, kvol = self._rulebook(f'l{i + 1}', B, coords, count, cap, shape, (3, 3, 3), (1, 1, 1), (1, 1, 1), True)
-        coords2, count2, cap2, shape2, nbr2, kv2 = self._rulebook('out', B, coords, count, cap, shape, self.k_out, (2, 1, 1), (0, 0, 0), False)
-        x = e.sparse_conv(x, self.w_out, nbr2, count2, cap2, kv2, e.buf('sp.out.x', (cap2, self.w_out.Cout)), act=ACT_RELU, name='conv_out')
+                    rb = self._rulebook(f'l{i + 1}', B, rd['coords'], rd['count'], rd['cap'], rd['shape'], (3, 3, 3), (1, 1, 1), (1, 1, 1), True)
+        ro = self._rulebook('out', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], self.k_out, (2, 1, 1), (0, 0, 0), False)
+        x = e.sparse_conv(x, self.w_out, ro, e.buf('sp.out.x', (ro['cap'], self.w_out.Cout)), act=ACT_RELU, name='conv_out')
+        coords2, count2, cap2, shape2 = ro['coords'], ro['count'], ro['cap'], ro['shape']
         D, H, W = shape2
         Cs = self.w_out.Cout
         dense = e.fmap('lidar.dense', B, H, W, Cs * D)
