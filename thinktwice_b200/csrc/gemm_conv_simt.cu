@@ -37,13 +37,11 @@ struct ConvArgs {
 constexpr int BK = 16;
 
 template <int BM, int BN, int TM, int TN, bool VECA, bool VECB>
-__global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
+__device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const int M, float (*As)[BK][BM], float (*Bs)[BK][BN]) {
   constexpr int NA = BM * BK / 256;          // A floats per thread per slab (8 or 4)
   constexpr int NB = BK * BN / 256;          // B floats per thread per slab (8 or 4)
   constexpr int QM = TM / 4, QN = TN / 4;
   constexpr int TX = BN / TN;
-  __shared__ __align__(16) float As[2][BK][BM];
-  __shared__ __align__(16) float Bs[2][BK][BN];
 
   const tt_conv_desc& d = p.d;
   const int tid = threadIdx.x;
@@ -51,11 +49,7 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
   const int sp = blockIdx.z - g * p.splits;
   const int k_begin = sp * p.k_per_split;
   const int k_end = min(p.Kg, k_begin + p.k_per_split);
-  const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
-  int M = p.M;
-  if (p.m_count) M = min(M, *p.m_count);
-  if (m0 >= M) return;
 
   // ---- A loader state: one output row per thread, NA consecutive k
   const int a_row = tid % BM;
@@ -284,6 +278,20 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
   }
 }
 
+// grid.x walks the M tiles with a grid stride, so a launch sized for a row CAPACITY (sparse rulebooks: the real row
+// count is a device scalar) does not pay for thousands of empty CTAs.
+template <int BM, int BN, int TM, int TN, bool VECA, bool VECB>
+__global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  int M = p.M;
+  if (p.m_count) M = min(M, *p.m_count);
+  for (int mt = blockIdx.x; mt * BM < M; mt += gridDim.x) {
+    conv_tile<BM, BN, TM, TN, VECA, VECB>(p, mt * BM, M, As, Bs);
+    __syncthreads();                           // the next tile reuses the shared-memory slabs
+  }
+}
+
 __global__ void splitk_reduce_kernel(const ConvArgs p) {
   const tt_conv_desc& d = p.d;
   int M = p.M;
@@ -316,7 +324,9 @@ __global__ void splitk_reduce_kernel(const ConvArgs p) {
 
 template <int BM, int BN, int TM, int TN>
 void launch_cfg(const ConvArgs& a, bool veca, bool vecb, cudaStream_t st) {
-  dim3 grid(tt_cdiv(a.M, BM), tt_cdiv(a.Cout_g, BN), a.d.groups * a.splits);
+  int gx = tt_cdiv(a.M, BM);
+  if (a.m_count && gx > 148 * 8) gx = 148 * 8;                  // capacity-sized launches: grid-stride over the tiles
+  dim3 grid(gx, tt_cdiv(a.Cout_g, BN), a.d.groups * a.splits);
   if (veca && vecb) conv_igemm_simt<BM, BN, TM, TN, true, true><<<grid, 256, 0, st>>>(a);
   else if (veca) conv_igemm_simt<BM, BN, TM, TN, true, false><<<grid, 256, 0, st>>>(a);
   else if (vecb) conv_igemm_simt<BM, BN, TM, TN, false, true><<<grid, 256, 0, st>>>(a);
@@ -331,9 +341,9 @@ int tt_simt_splits(const tt_conv_desc* d, int has_gather) {
   const int M = has_gather ? d->M : d->N * d->OH * d->OW;
   const int Kg = taps * (d->Cin / d->groups);
   const long long tiles = (long long)tt_cdiv(M, 64) * tt_cdiv(d->Cout / d->groups, 64) * d->groups;
-  if (has_gather || tiles >= 74 || Kg < 1024) return 1;
+  if (has_gather || tiles >= 74 || Kg < 256) return 1;
   int s = tt_cdiv(296, tiles);
-  if (s > Kg / 256) s = Kg / 256;
+  if (s > Kg / 64) s = Kg / 64;
   if (s > 32) s = 32;
   return s < 2 ? 1 : s;
 }
