@@ -69,7 +69,13 @@ def cpu_oracle_worker(max_frames):
     from thinktwice_b200.synthetic import make_batch
     cfg = Config.fromfile(DEFAULT_CONFIG)
     torch.set_flush_denormal(True)
-    print(f'THREADS {torch.get_num_threads()}', flush=True)      # torch's default intra-op pool for this host / cgroup
+    try:                                                         # all physical cores (torchrun pins OMP_NUM_THREADS=1 for its children)
+        import psutil
+        ncores = psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        ncores = max(1, (os.cpu_count() or 2) // 2)
+    torch.set_num_threads(ncores)
+    print(f'THREADS {torch.get_num_threads()}', flush=True)
     oracle = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'}).eval()
     init_oracle_weights(oracle, 0)
     batch = make_batch(cfg, 1, seed=0)
@@ -85,8 +91,9 @@ def cpu_oracle_worker(max_frames):
 
 def cpu_oracle(max_frames, budget_s):
     """frames/s of the CPU restatement on a bounded sample (<= max_frames B=1 frames, <= budget_s seconds)."""
+    env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS')}
     p = subprocess.Popen([sys.executable, os.path.abspath(__file__), '--impl', 'reference-worker', '--steps', str(max_frames)],
-                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
     frames, threads, warm = [], None, None
     deadline = time.time() + budget_s
 
