@@ -15,12 +15,15 @@ def relerr(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
-def build_pair(cfg_path, B, num_points, seed=0, impl=1):
+def build_pair(cfg_path, B, num_points, seed=0, impl=1, refine_num=None):
     from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
     from thinktwice_b200.config import Config
     from thinktwice_b200.registry import build_model
     from thinktwice_b200.synthetic import make_batch
     cfg = Config.fromfile(cfg_path)
+    if refine_num is not None:                                      # BASELINE.json configs[4]: decoder-depth sweep
+        for c in (cfg.model.decoder.config, cfg.model.train_cfg, cfg.model.test_cfg):
+            c['refine_num'] = refine_num
     oracle = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'})
     init_oracle_weights(oracle, seed)
     batch = make_batch(cfg, B, seed=seed, num_points=num_points)
@@ -76,6 +79,15 @@ def test_repeat_forward_is_bitwise_stable_where_deterministic():
     a = model.forward_inference(batch)['pred_wp'].clone()
     b = model.forward_inference(batch)['pred_wp'].clone()
     assert float((a - b).abs().max()) < 1e-4 * float(a.abs().max())
+
+
+@pytest.mark.parametrize('K', [2, 3])
+def test_decoder_depth_sweep_matches_oracle(K):
+    """BASELINE.json configs[4] (K in {1,2,3,5,10}): K=1 and K=5 are the plumbing / full configs, here K=2,3."""
+    from thinktwice_b200.config import PLUMBING_CONFIG
+    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 1000, seed=3, impl=3, refine_num=K)
+    errs = compare_all(oracle, model, batch)
+    assert oracle.decoder.config['refine_num'] == K and len(model.decoder.layers) == K
 
 
 def test_cuda_graph_replay_equals_eager():

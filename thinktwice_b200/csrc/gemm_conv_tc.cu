@@ -62,6 +62,25 @@ TT_DEVICE void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// weight half-tile loaded by this CTA and delivered to BOTH CTAs of the pair (same smem offset, same mbarrier offset)
+TT_DEVICE void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// MMA completion signalled to the same barrier in both CTAs of the pair (the stage holds a multicast operand)
+TT_DEVICE void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+TT_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+TT_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 TT_DEVICE void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -147,7 +166,11 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long lo
   }
 }
 
-// Persistent, warp-specialised kernel: each CTA (one per SM) walks tiles t = blockIdx.x, += gridDim.x.  The smem
+// CTA PAIRS (thread-block cluster of 2, one TPC): the two CTAs work on two different M tiles of the SAME N tile in
+// lockstep; each loads half of the weight slab and TMA-multicasts it into both CTAs' shared memory, halving the
+// weight traffic from L2 (the kernel's measured roof is L2->SM bandwidth).  A stage is refilled only after BOTH
+// MMA threads released it (multicast tcgen05.commit onto both CTAs' `empty` barriers, count 2).
+// Persistent, warp-specialised kernel: each CTA pair walks tile pairs pt = blockIdx.x / 2, += gridDim.x / 2.  The smem
 // ring, the TMEM ping-pong and all phase counters run ACROSS tiles, so while the epilogue warps store tile i the
 // TMA and MMA warps are already deep into tile i + 1.
 template <int BN>
@@ -180,10 +203,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int taps = d.KH * d.KW;
   const int k_iters = taps * p.n_slabs;
   const int n_chunks = (k_iters + p.chunk - 1) / p.chunk;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = cluster_ctarank();                // 0 / 1 inside the CTA pair
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int total_pairs = m_pairs * p.n_tiles;              // both CTAs iterate the same pair list (lockstep)
+  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }       // empty: both MMA threads of the pair
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }   // 8 epilogue warps arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -193,6 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();                                       // the peer's barriers are initialised before any multicast lands
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -200,10 +227,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================================================================== TMA producer
     if (lane == 0) {
       const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KS * 4;   // bytes one activation box delivers
-      const uint32_t tx = (p.terms == 3 ? 2 : 1) * (((p.dbg & 2) ? 0u : a_box) + B_BYTES);
+      const uint32_t tx = (p.terms == 3 ? 2 : 1) * (((p.dbg & 2) ? 0u : a_box) + B_BYTES);   // own A + both weight halves
       int ig = 0;                                                               // ring position, continues across tiles
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+        const int nt = pt % p.n_tiles, mt = 2 * (pt / p.n_tiles) + (int)rank;     // mt >= m_tiles: dummy tile, TMA zero-fills
         const int n0 = nt * BN;
         int cw0, ch0, cn;
         if (p.flat) { cw0 = mt * BM; ch0 = 0; cn = 0; }
@@ -221,10 +248,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_expect_tx(&full[s], tx);
           const int cw = p.flat ? cw0 : cw0 + kw * d.dil, ch = p.flat ? 0 : ch0 + kh * d.dil;
           if (!(p.dbg & 2)) tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
-          tma_load_3d(st + 2 * A_BYTES, &map_b_hi, &full[s], slab * KS, tap, n0);
+          tma_load_3d_mc(st + 2 * A_BYTES + rank * (B_BYTES / 2), &map_b_hi, &full[s], slab * KS, tap, n0 + (int)rank * (BN / 2), 3);
           if (p.terms == 3) {
             if (!(p.dbg & 2)) tma_load_4d(st + A_BYTES, &map_a_lo, &full[s], slab * KS, cw, ch, cn);
-            tma_load_3d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, &full[s], slab * KS, tap, n0);
+            tma_load_3d_mc(st + 2 * A_BYTES + B_BYTES + rank * (B_BYTES / 2), &map_b_lo, &full[s], slab * KS, tap, n0 + (int)rank * (BN / 2), 3);
           }
         }
       }
@@ -234,7 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       int ig = 0, cg = 0;                                                       // ring / chunk counters across tiles
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int pt = pair0; pt < total_pairs; pt += pair_step) {
         int it = 0;
         for (int c = 0; c < n_chunks; ++c, ++cg) {
           const int b = cg & 1;
@@ -261,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               }
             }
             first = false;
-            tcgen05_commit(&empty[s]);                       // frees the smem slot once these MMAs retire
+            tcgen05_commit_mc(&empty[s], 3);                 // releases the slot in BOTH CTAs once these MMAs retire
           }
           tcgen05_commit(&acc_full[b]);                      // chunk complete -> epilogue may drain
         }
@@ -277,8 +304,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int HWo = d.OH * d.OW;
     float* tile = tile_all + (warp - 2) * 32 * PITCH;      // warp-private transposition buffer [32 rows][PITCH]
     int cg = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+    for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+      const int nt = pt % p.n_tiles, mt = 2 * (pt / p.n_tiles) + (int)rank;
+      const bool real_tile = mt < p.m_tiles;
       const int n0 = nt * BN + half * HN;
       // ---- this thread's row -> output / residual addresses (once per tile); prefetch the residual lines into L2
       {
@@ -287,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         long long rrow;
         if (p.flat) {
           const long long pix = (long long)mt * BM + r;
-          valid = pix < p.total_pix;
+          valid = real_tile && pix < p.total_pix;
           nimg = (int)(pix / HWo);
           const int rem = (int)(pix - (long long)nimg * HWo);
           oh = rem / d.OW; ow = rem - oh * d.OW;
@@ -297,7 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           nimg = mt / (p.tiles_w * p.tiles_h);
           const int rh = r / p.TW, rw = r - rh * p.TW;
           oh = th * p.TH + rh; ow = tw * p.TW + rw;
-          valid = (r < p.TH * p.TW) && oh < d.OH && ow < d.OW;
+          valid = real_tile && (r < p.TH * p.TW) && oh < d.OH && ow < d.OW;
           rrow = ((long long)nimg * d.OH + oh) * d.OW + ow;
         }
         const long long r1 = (d.res_mode == TT_RES_UP2_NEAREST
@@ -395,6 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();                                       // no CTA leaves while its peer can still signal its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
@@ -520,7 +549,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     const size_t wplane = (size_t)d->Cout * taps * d->Cin;
     cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)taps, (cuuint64_t)d->Cout};
     cuuint64_t str[2] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)taps * d->Cin * 4};
-    cuuint32_t box[3] = {KS, 1, (cuuint32_t)BN};
+    cuuint32_t box[3] = {KS, 1, (cuuint32_t)(BN / 2)};               // each CTA of a pair loads (and multicasts) half of the slab
     if (!encode_map(&mb_hi, w_tc, 3, dims, str, box)) return TT_ERR_CUDA;
     if (!encode_map(&mb_lo, w_tc + wplane, 3, dims, str, box)) return TT_ERR_CUDA;
   }
@@ -529,19 +558,31 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.n_tiles = tt_cdiv(d->Cout, BN);
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-  const long long tiles = (long long)a.m_tiles * a.n_tiles;
-  dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));          // persistent: one CTA per SM
+  const long long pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles;
+  const long long max_pairs = num_sms / 2;
+  dim3 grid((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));  // persistent CTA pairs (cluster of 2), one CTA per SM
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 256;  // 8 warp-private slabs + row tables + barriers
   if (BN == 128) {
     constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;
     if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
-    conv_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+    cfg.dynamicSmemBytes = smem;
+    if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<128>, ma_hi, ma_lo, mb_hi, mb_lo, a) != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TT_ERR_CUDA; }
   } else {
     constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
-    conv_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+    cfg.dynamicSmemBytes = smem;
+    if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<64>, ma_hi, ma_lo, mb_hi, mb_lo, a) != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TT_ERR_CUDA; }
   }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_conv2d(tc)");
