@@ -29,7 +29,6 @@ namespace {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int KS = 32;           // floats per K slab (one 128-byte swizzle row)
-constexpr int STAGES = 3;
 constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -173,7 +172,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long lo
 // Persistent, warp-specialised kernel: each CTA pair walks tile pairs pt = blockIdx.x / 2, += gridDim.x / 2.  The smem
 // ring, the TMEM ping-pong and all phase counters run ACROSS tiles, so while the epilogue warps store tile i the
 // TMA and MMA warps are already deep into tile i + 1.
-template <int BN>
+template <int BN, int STAGES, bool MERGED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
@@ -181,7 +180,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr int A_BYTES = BM * KS * 4;                    // 16 KB
   constexpr int B_BYTES = BN * KS * 4;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr int TMEM_COLS = 4 * BN;                       // 2 (ping-pong) x {main, corr} x BN fp32 columns
+  // TMEM: 2 (ping-pong) x {main, corr} x BN fp32 columns; MERGED (BN = 256): the correction products share the main
+  // accumulator (2 x BN columns) and chunks are shorter instead, so the truncating accumulations per chunk stay ~24.
+  constexpr int ACC_COLS = MERGED ? BN : 2 * BN;
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
   constexpr int SLAB = 16;                                // epilogue slab: 16 columns of a warp's 32 rows
   constexpr int PITCH = SLAB + 4;                         // +4 floats: conflict-free transposition
   constexpr int HN = BN / 2;                              // columns owned by one epilogue warp (column half)
@@ -267,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int b = cg & 1;
           mbar_wait(&acc_empty[b], ((cg >> 1) & 1) ^ 1);     // epilogue has drained this accumulator pair
           tcgen05_fence_after();
-          const uint32_t t_main = tmem_base + (uint32_t)(b * 2 * BN), t_corr = t_main + BN;
+          const uint32_t t_main = tmem_base + (uint32_t)(b * ACC_COLS), t_corr = MERGED ? t_main : t_main + BN;
           const int it_end = min(it + p.chunk, k_iters);
           bool first = true;
           for (; it < it_end; ++it, ++ig) {
@@ -283,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const uint32_t acc = (first && kk == 0) ? 0u : 1u;
               umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
               if (p.terms == 3) {
-                umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, acc);
+                umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, MERGED ? 1u : acc);
                 umma_tf32(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
               }
             }
@@ -356,12 +358,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int b = cg & 1;
         mbar_wait(&acc_full[b], (cg >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * 2 * BN + half * HN);
+        const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * ACC_COLS + half * HN);
 #pragma unroll
         for (int c0 = 0; c0 < HN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_main + c0, v);
-          if (p.terms == 3) {
+          if (p.terms == 3 && !MERGED) {
             uint32_t u[32];
             tmem_ld32(t_main + BN + c0, u);
 #pragma unroll
@@ -510,7 +512,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.d = *d;
   a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
   a.terms = terms;
-  a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk
+  a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk (set to 2 for BN = 256)
   a.n_slabs = (d->Cin + KS - 1) / KS;
   a.total_pix = d->N * d->OH * d->OW;
   a.flat = (taps == 1 && d->pad == 0 && d->stride == 1) ? 1 : 0;
@@ -544,7 +546,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
     grid_x = a.tiles_w * a.tiles_h * d->N;
   }
-  const int BN = d->Cout > 64 ? 128 : 64;
+  const int BN = d->Cout >= 256 && terms == 3 ? 256 : (d->Cout > 64 ? 128 : 64);   // wider tiles: fewer operand bytes per MMA
   {
     const size_t wplane = (size_t)d->Cout * taps * d->Cin;
     cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)taps, (cuuint64_t)d->Cout};
@@ -571,19 +573,28 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 256;  // 8 warp-private slabs + row tables + barriers
-  if (BN == 128) {
-    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
+  cudaError_t lerr;
+  if (BN == 256) {
+    a.chunk = 2;
+    constexpr int smem = 2 * (2 * BM * KS * 4 + 2 * 256 * KS * 4) + 1024 + EPI_BYTES;
+    static bool set256 = false;
+    if (!set256) { cudaFuncSetAttribute(conv_tc_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set256 = true; }
+    cfg.dynamicSmemBytes = smem;
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, 2, true>, ma_hi, ma_lo, mb_hi, mb_lo, a);
+  } else if (BN == 128) {
+    constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;
-    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
+    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
     cfg.dynamicSmemBytes = smem;
-    if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<128>, ma_hi, ma_lo, mb_hi, mb_lo, a) != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TT_ERR_CUDA; }
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false>, ma_hi, ma_lo, mb_hi, mb_lo, a);
   } else {
-    constexpr int smem = STAGES * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
+    constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
     static bool set64 = false;
-    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
+    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
     cfg.dynamicSmemBytes = smem;
-    if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<64>, ma_hi, ma_lo, mb_hi, mb_lo, a) != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TT_ERR_CUDA; }
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false>, ma_hi, ma_lo, mb_hi, mb_lo, a);
   }
+  if (lerr != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_conv2d(tc)");
   return TT_OK;
