@@ -546,7 +546,10 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
     grid_x = a.tiles_w * a.tiles_h * d->N;
   }
-  const int BN = d->Cout >= 256 && terms == 3 ? 256 : (d->Cout > 64 ? 128 : 64);   // wider tiles: fewer operand bytes per MMA
+  // BN = 256 (fewer activation bytes per MMA, but a 2-stage ring and a heavier epilogue) pays off only for long-K
+  // layers with enough tiles to fill the machine (measured: 3x3 512->512 @28x56 218 -> 185 us; 1x1 layers lose).
+  const bool wide = terms == 3 && d->Cout >= 256 && taps >= 9 && d->Cin >= 256 && (long long)grid_x * tt_cdiv(d->Cout, 256) >= 74;
+  const int BN = wide ? 256 : (d->Cout > 64 ? 128 : 64);
   {
     const size_t wplane = (size_t)d->Cout * taps * d->Cin;
     cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)taps, (cuuint64_t)d->Cout};
