@@ -89,13 +89,14 @@ int tt_lift_splat(const tt_lift_splat_desc* d, const float* depth_logits, const 
  *   g*Cin_g + c, zero outside the image; or, when gather != NULL, row gather[m*taps + tap] of x
  *   (-1 = zero row) — the sparse-conv rulebook.
  *   w: impl 0/1: packed [taps * Cin_g][Cout] fp32 (BatchNorm already folded in); impl 2/3 (tcgen05): packed
- *      [2][Cout][taps][Cin] = TF32-exact `hi` plane followed by the `lo = w - hi` plane.  bias [Cout] or NULL.
+ *      [2][Cout][taps][Cin] = `hi = RN_tf32(w)` plane followed by the `lo = RN_tf32(w - hi)` plane.  bias [Cout] or NULL.
  * Output row m = (n, oh, ow) is stored at pixel (n, oh*oy_mul + oy_add, ow*ox_mul + ox_add) of a
  * [N][yH][yW][y_ld] buffer (a k2s2 transposed conv is four such calls).
  * If m_count != NULL only the first *m_count rows (a device int) are computed.
  * `impl`: 0/1 = SIMT fp32 FFMA (exact), 2 = tcgen05 single-pass TF32 (operands rounded to nearest TF32),
- *         3 = tcgen05 3xTF32 (hi*hi + hi*lo + lo*hi, fp32-class).  impl 2/3 need stride 1, groups 1, channels % 4 == 0
- *         and `workspace` of tt_conv2d_workspace_bytes(d) bytes (TF32 split planes of the input); else TT_ERR_UNSUPPORTED.
+ *         3 = tcgen05 3xTF32 (hi*hi + hi*lo + lo*hi, fp32-class).  impl 2/3 need stride 1 or 2, groups 1, channels,
+ *         x_ld, x_coff % 4 == 0 and 16-byte aligned x / w / y (TMA reads the activations in place and splits them in
+ *         shared memory; no workspace); else TT_ERR_UNSUPPORTED.
  *         For impl 0/1 the workspace is optional: when given (size from tt_conv2d_workspace_bytes) small-M / large-K
  *         layers run split-K with a deterministic fixed-order reduction.
  */

@@ -42,7 +42,6 @@ int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float
       tt_set_error("tt_conv2d: tcgen05 path does not support this shape / alignment");
       return TT_ERR_UNSUPPORTED;
     }
-    TT_REQUIRE(workspace != nullptr, "tt_conv2d", "tcgen05 path needs tt_conv2d_workspace_bytes() of workspace");
     return tt_conv2d_tc(d, x, w, bias, res, res2, y, workspace, st);
   }
   return tt_conv2d_simt(d, x, w, bias, res, res2, gather, m_count, y, workspace, st);

@@ -7,6 +7,9 @@
 //     channels are zero-filled by the TMA unit, so padding / dilation cost nothing;
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x BN x K8) with the fp32
 //     accumulator tile living in TMEM (BN columns x 128 lanes);
+//   * the raw fp32 activation slab is what TMA delivers; two "split" warps rewrite it in shared memory as hi (in place)
+//     and lo (second buffer) before the MMA thread may touch it — no pre-pass over the activations, no lo plane
+//     streamed from L2 (the kernel's roof is L2->SM ingest: profiles/r1_summary_tc.md);
 //   * precision: fp32 operands are split x = hi + lo with hi, lo both TF32-representable (round-to-nearest), and
 //     every K slab issues hi*hi + hi*lo + lo*hi ("3xTF32": ~21 mantissa bits per operand).  The tensor core adds
 //     into its fp32 accumulator with truncation, an error that grows linearly with the number of accumulations
@@ -29,7 +32,7 @@ namespace {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int KS = 32;           // floats per K slab (one 128-byte swizzle row)
-constexpr int NTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+constexpr int NTHREADS = 384;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter), warps 10..11 operand split
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 TT_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,28 +144,21 @@ struct TcArgs {
   int m_tiles, n_tiles;  // persistent tile walk: tile t -> (m tile t / n_tiles, n tile t % n_tiles)
 };
 
-// operand split: hi = RN_tf32(x), lo = RN_tf32(x - hi); both exactly representable in TF32, so the tensor core's
-// own fp32->tf32 conversion (truncation) is exact and no rounding bias enters the products.
-__global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long long x_nstride, int HW, int C4,
-                                  float4* __restrict__ hi, float4* __restrict__ lo, long long total, int rn) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = i % C4;
-    const long long pix = i / C4;
-    const long long n = pix / HW, p = pix % HW;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + n * x_nstride + p * x_ld) + c4);
-    float e[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t u = __float_as_uint(e[j]);
-      u += 0xFFFu + ((u >> 13) & 1u);                        // round-to-nearest-even at TF32 precision
-      h[j] = __uint_as_float(u & 0xFFFFE000u);
-      uint32_t v = __float_as_uint(e[j] - h[j]);             // exact in fp32
-      v += 0xFFFu + ((v >> 13) & 1u);
-      l[j] = __uint_as_float(v & 0xFFFFE000u);
-    }
-    hi[i] = make_float4(h[0], h[1], h[2], h[3]);
-    if (lo) lo[i] = make_float4(l[0], l[1], l[2], l[3]);
-  }
+// operand split used by the in-kernel split warps: hi = x rounded to nearest TF32 (ties away: one IADD + one LOP3 on
+// the alu pipe), lo = x - hi (exact in fp32, one FADD on the fma pipe).  |lo| <= 2^-11 |x| with either sign, so the
+// tensor core's own fp32 -> tf32 truncation of lo is an unbiased 2^-21-relative perturbation.  Anything heavier makes the
+// two split warps the bottleneck: the alu pipe issues one warp instruction per 2 clocks per SM sub-partition.
+TT_DEVICE float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+TT_DEVICE void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+TT_DEVICE void split_rn(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
 }
 
 // CTA PAIRS (thread-block cluster of 2, one TPC): the two CTAs work on two different M tiles of the SAME N tile in
@@ -174,8 +170,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int x_ld, long lo
 // TMA and MMA warps are already deep into tile i + 1.
 template <int BN, int STAGES, bool MERGED>
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+               const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = BM * KS * 4;                    // 16 KB
   constexpr int B_BYTES = BN * KS * 4;
@@ -194,11 +190,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   long long* row_r2 = row_r1 + BM;                                                      // [128] residual-2 pixel (= GEMM row)
   int* row_flag = reinterpret_cast<int*>(row_r2 + BM);                                  // [128] valid | image << 1
   uint64_t* bars = reinterpret_cast<uint64_t*>(row_flag + BM);
-  uint64_t* full = bars;                                  // [STAGES]  TMA -> MMA
+  uint64_t* full = bars;                                  // [STAGES]  TMA -> split warps (raw operands landed)
   uint64_t* empty = bars + STAGES;                        // [STAGES]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * STAGES;                 // [2]       MMA -> epilogue (chunk finished)
-  uint64_t* acc_empty = bars + 2 * STAGES + 2;            // [2]       epilogue -> MMA (accumulators drained)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* conv = bars + 2 * STAGES;                     // [STAGES]  split warps -> MMA (hi / lo written)
+  uint64_t* acc_full = bars + 3 * STAGES;                 // [2]       MMA -> epilogue (chunk finished)
+  uint64_t* acc_empty = bars + 3 * STAGES + 2;            // [2]       epilogue -> MMA (accumulators drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const tt_conv_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }       // empty: both MMA threads of the pair
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); mbar_init(&conv[s], 2); }   // empty: both MMA threads of the pair; conv: 2 split warps
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }   // 8 epilogue warps arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -229,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================================================================== TMA producer
     if (lane == 0) {
       const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KS * 4;   // bytes one activation box delivers
-      const uint32_t tx = (p.terms == 3 ? 2 : 1) * (((p.dbg & 2) ? 0u : a_box) + B_BYTES);   // own A + both weight halves
+      const uint32_t tx = ((p.dbg & 2) ? 0u : a_box) + (p.terms == 3 ? 2 : 1) * B_BYTES;     // own raw A + both weight halves
       int ig = 0;                                                               // ring position, continues across tiles
       for (int pt = pair0; pt < total_pairs; pt += pair_step) {
         const int nt = pt % p.n_tiles, mt = 2 * (pt / p.n_tiles) + (int)rank;     // mt >= m_tiles: dummy tile, TMA zero-fills
@@ -249,10 +246,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int kh = tap / d.KW, kw = tap - kh * d.KW;
           mbar_expect_tx(&full[s], tx);
           const int cw = p.flat ? cw0 : cw0 + kw * d.dil, ch = p.flat ? 0 : ch0 + kh * d.dil;
-          if (!(p.dbg & 2)) tma_load_4d(st, &map_a_hi, &full[s], slab * KS, cw, ch, cn);
+          if (!(p.dbg & 2)) tma_load_4d(st, &map_a, &full[s], slab * KS, cw, ch, cn);      // raw fp32 activations
           tma_load_3d_mc(st + 2 * A_BYTES + rank * (B_BYTES / 2), &map_b_hi, &full[s], slab * KS, tap, n0 + (int)rank * (BN / 2), 3);
           if (p.terms == 3) {
-            if (!(p.dbg & 2)) tma_load_4d(st + A_BYTES, &map_a_lo, &full[s], slab * KS, cw, ch, cn);
             tma_load_3d_mc(st + 2 * A_BYTES + B_BYTES + rank * (B_BYTES / 2), &map_b_lo, &full[s], slab * KS, tap, n0 + (int)rank * (BN / 2), 3);
           }
         }
@@ -274,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           bool first = true;
           for (; it < it_end; ++it, ++ig) {
             const int s = ig % STAGES;
-            mbar_wait(&full[s], (ig / STAGES) & 1);
+            mbar_wait(&conv[s], (ig / STAGES) & 1);         // operands landed AND split into hi / lo
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
             const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
@@ -294,6 +290,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
           tcgen05_commit(&acc_full[b]);                      // chunk complete -> epilogue may drain
         }
+      }
+    }
+  } else if (warp >= 10) {
+    // ===================================================================== operand split (warps 10, 11)
+    // Each warp owns 64 rows of the 128 x 32-float activation slab: raw -> hi in place, lo into the second buffer.
+    // Element-wise at identical offsets, so the 128-byte swizzle TMA applied is irrelevant here.
+    const int w2 = warp - 10;
+    int ig = 0;
+    for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+      for (int it = 0; it < k_iters; ++it, ++ig) {
+        const int s = ig % STAGES;
+        mbar_wait(&full[s], (ig / STAGES) & 1);
+        const uint32_t raw = smem_u32(smem + s * STAGE_BYTES) + w2 * (A_BYTES / 2) + lane * 16;   // lo at + A_BYTES
+        // all loads of a batch are issued before any store: the loop is latency-bound otherwise (16 dependent
+        // ld -> alu -> st round trips per stage per lane)
+#pragma unroll
+        for (int b0 = 0; b0 < A_BYTES / 32 / 32; b0 += 8) {    // 16 float4 per lane, two batches of 8
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = lds128(raw + (b0 + u) * 512);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 h, l;
+            split_rn(v[u].x, h.x, l.x); split_rn(v[u].y, h.y, l.y); split_rn(v[u].z, h.z, l.z); split_rn(v[u].w, h.w, l.w);
+            sts128(raw + (b0 + u) * 512, h);
+            if (p.terms == 3) sts128(raw + A_BYTES + (b0 + u) * 512, l);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv[s])) : "memory");
       }
     }
   } else {
@@ -462,13 +489,11 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
   return true;
 }
 
-inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
-
 }  // namespace
 
 bool tt_conv2d_tc_supported(const tt_conv_desc* d, const void* x, const void* w, const void* y) {
   if (d->groups != 1 || (d->stride != 1 && d->stride != 2)) return false;
-  if (d->Cin % 4 || d->Cout % 4 || d->x_ld % 4 || d->y_ld % 4 || d->x_nstride % 4 || d->y_nstride % 4) return false;
+  if (d->Cin % 4 || d->Cout % 4 || d->x_ld % 4 || d->x_coff % 4 || d->y_ld % 4 || d->x_nstride % 4 || d->y_nstride % 4) return false;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return false;
   if (d->res_mode != TT_RES_NONE && (d->res_ld % 4)) return false;
   if (d->res2_ld % 4) return false;
@@ -485,29 +510,17 @@ extern "C" size_t tt_conv2d_workspace_bytes(const tt_conv_desc* d) {
     const int s = tt_simt_splits(d, 0);
     return s > 1 ? (size_t)s * d->N * d->OH * d->OW * d->Cout * 4 : 0;
   }
-  const size_t plane = al256((size_t)d->N * d->H * d->W * d->Cin * 4);
-  return (d->impl == 3 ? 2 : 1) * plane;
+  return 0;                                                   // tcgen05: operands are split inside the kernel
 }
 
-// w_tc: [2][Cout][taps][Cin] fp32 = explicit hi plane then lo plane (prepared once per layer by the host).
+// w_tc: [2][Cout][taps][Cin] fp32 = TF32-exact hi plane then lo plane (prepared once per layer by the host).
 int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const float* bias, const float* res,
-                 const float* res2, float* y, void* workspace, cudaStream_t st) {
+                 const float* res2, float* y, void* /*workspace*/, cudaStream_t st) {
   const int terms = d->impl == 3 ? 3 : 1;
   const int taps = d->KH * d->KW;
   const long long npix_in = (long long)d->N * d->H * d->W;
-  const size_t plane = al256((size_t)npix_in * d->Cin * 4);
-  float* a_hi = static_cast<float*>(workspace);
-  float* a_lo = terms == 3 ? reinterpret_cast<float*>(static_cast<char*>(workspace) + plane) : nullptr;
-  {
-    const long long total = npix_in * (d->Cin / 4);
-    const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * d->W * d->x_ld;
-    const long long nb = (total + 255) / 256;
-    split_tf32_kernel<<<(int)(nb > 148 * 16 ? 148 * 16 : nb), 256, 0, st>>>(x + d->x_coff, d->x_ld, xns, d->H * d->W, d->Cin / 4,
-                                                                         reinterpret_cast<float4*>(a_hi), reinterpret_cast<float4*>(a_lo),
-                                                                         total, terms == 1);
-    ++g_tt_launches;
-    TT_CHECK_LAUNCH("tt_conv2d(tc split)");
-  }
+  const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * d->W * d->x_ld;
+  const float* xa = x + d->x_coff;                            // TMA reads the activation tensor in place (ld / coff / image stride)
   TcArgs a;
   a.d = *d;
   a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
@@ -515,16 +528,15 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk (set to 2 for BN = 256)
   a.n_slabs = (d->Cin + KS - 1) / KS;
   a.total_pix = d->N * d->OH * d->OW;
-  a.flat = (taps == 1 && d->pad == 0 && d->stride == 1) ? 1 : 0;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  a.flat = (taps == 1 && d->pad == 0 && d->stride == 1 && xns == (long long)d->H * d->W * d->x_ld) ? 1 : 0;
+  CUtensorMap ma, mb_hi, mb_lo;
   int grid_x;
   if (a.flat) {
     a.TH = 1; a.TW = BM; a.tiles_w = a.tiles_h = 1;
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)npix_in, 1, 1};
-    cuuint64_t str[3] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)npix_in * d->Cin * 4, (cuuint64_t)npix_in * d->Cin * 4};
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)npix_in, 1, 1};       // dim 0 = logical channels: beyond Cin is zero-filled
+    cuuint64_t str[3] = {(cuuint64_t)d->x_ld * 4, (cuuint64_t)npix_in * d->x_ld * 4, (cuuint64_t)npix_in * d->x_ld * 4};
     cuuint32_t box[4] = {KS, BM, 1, 1};
-    if (!encode_map(&ma_hi, a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
-    if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box)) return TT_ERR_CUDA;
+    if (!encode_map(&ma, xa, 4, dims, str, box)) return TT_ERR_CUDA;
     grid_x = tt_cdiv(npix_in, BM);
   } else {
     // rectangle with TH * TW <= 128 that wastes the fewest rows
@@ -540,10 +552,9 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     a.TH = best_th; a.TW = best_tw;
     a.tiles_w = tt_cdiv(d->OW, a.TW); a.tiles_h = tt_cdiv(d->OH, a.TH);
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t str[3] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)d->W * d->Cin * 4, (cuuint64_t)d->H * d->W * d->Cin * 4};
+    cuuint64_t str[3] = {(cuuint64_t)d->x_ld * 4, (cuuint64_t)d->W * d->x_ld * 4, (cuuint64_t)xns * 4};
     cuuint32_t box[4] = {KS, (cuuint32_t)(a.TW * d->stride), (cuuint32_t)(a.TH * d->stride), 1};
-    if (!encode_map(&ma_hi, a_hi, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
-    if (!encode_map(&ma_lo, terms == 3 ? a_lo : a_hi, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
+    if (!encode_map(&ma, xa, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
     grid_x = a.tiles_w * a.tiles_h * d->N;
   }
   // BN = 256 (fewer activation bytes per MMA, but a 2-stage ring and a heavier epilogue) pays off only for long-K
@@ -575,7 +586,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 256;  // 8 warp-private slabs + row tables + barriers
+  constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 256;  // 8 warp-private slabs + row tables + barriers (13 x 8 B)
   cudaError_t lerr;
   if (BN == 256) {
     a.chunk = 2;
@@ -583,19 +594,19 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     static bool set256 = false;
     if (!set256) { cudaFuncSetAttribute(conv_tc_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set256 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, 2, true>, ma_hi, ma_lo, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, 2, true>, ma, mb_hi, mb_lo, a);
   } else if (BN == 128) {
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;
     if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false>, ma_hi, ma_lo, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false>, ma, mb_hi, mb_lo, a);
   } else {
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false>, ma_hi, ma_lo, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false>, ma, mb_hi, mb_lo, a);
   }
   if (lerr != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;

@@ -55,7 +55,7 @@ class Engine:
         self.device = torch.device(device)
         self.impl = impl
         self.bufs = {}
-        self.tc_ws = None           # grow-only workspace of the tcgen05 path (TF32 split planes)
+        self.tc_ws = None           # grow-only conv workspace (split-K partial sums of the SIMT kernel)
         self.tc_min_rows = 512
         self.tc_strides = (1, 2)
         self.prof = None            # bench.py: list of (name, flops, start_event, end_event) per conv launch
@@ -131,7 +131,7 @@ class Engine:
                   and d.N * OH * OW >= self.tc_min_rows and pw.Cout >= 32)
         d.impl = impl if use_tc else lib.IMPL_SIMT
         ws = None
-        need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # TC: TF32 split planes; SIMT: split-K partials (or 0)
+        need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # SIMT: split-K partials; tcgen05: 0
         if need:
             if self.tc_ws is None or self.tc_ws.numel() < need:
                 self.tc_ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)

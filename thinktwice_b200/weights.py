@@ -15,15 +15,18 @@ def bn_affine(sd, n, eps):
     return s, t
 
 
-def tf32_split(w, rn=False):
-    """w (fp32) -> (hi, lo): hi is exactly TF32 (13 low mantissa bits clear), lo = w - hi (exact).
-    rn=True rounds hi to nearest-even TF32 instead of truncating (single-pass TF32 mode)."""
+def _rn_tf32(w):
+    u = w.contiguous().view(torch.int32)
+    u = u + 0xFFF + ((u >> 13) & 1)
+    return (u & ~0x1FFF).view(torch.float32)
+
+
+def tf32_split(w, rn=True):
+    """w (fp32) -> (hi, lo) with hi = RN_tf32(w), lo = RN_tf32(w - hi): both exactly TF32-representable — the same
+    split the tcgen05 kernel applies to the activations in shared memory (csrc/gemm_conv_tc.cu: split_rn)."""
     w = w.float().contiguous()
-    u = w.view(torch.int32)
-    if rn:
-        u = u + 0xFFF + ((u >> 13) & 1)
-    hi = (u & ~0x1FFF).view(torch.float32)
-    return hi, w - hi
+    hi = _rn_tf32(w)
+    return hi, _rn_tf32(w - hi)
 
 
 class Packer:
@@ -37,7 +40,7 @@ class Packer:
         Cout, taps, Cin = w_ohwi.shape
         if self.tc_mode not in (2, 3) or Cin % 4 or Cout % 4 or Cout < 32:
             return None
-        hi, lo = tf32_split(w_ohwi.float(), rn=(self.tc_mode == 2))
+        hi, lo = tf32_split(w_ohwi.float())
         return torch.stack([hi, lo]).contiguous().to(self.device)
 
     def _dev(self, t):
