@@ -31,13 +31,26 @@ struct ConvArgs {
   int splits, k_per_split;   // split-K (small-M / large-K layers): partial sums go to `partial`, reduced by a 2nd kernel
   float* partial;            // [splits][M][Cout]
   const int* out_index;      // gather mode: output row of GEMM row m (tap-major sparse conv pairs); NULL = m
-  int accumulate;            // gather mode: y[row] += result (rows of one launch are distinct)
+  int accumulate;            // gather mode: 1: y[row] += result (rows of one launch are distinct); 2: atomic (red.add)
 };
+
+// what differs between the work items of one launch (the fused sparse conv walks (tap, row tile, column tile) items)
+struct TileSel {
+  const float* w;
+  const int* gather;
+  const int* out_index;
+  int n_tile;
+};
+
+TT_DEVICE void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 constexpr int BK = 16;
 
 template <int BM, int BN, int TM, int TN, bool VECA, bool VECB>
-__device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const int M, float (*As)[BK][BM], float (*Bs)[BK][BN]) {
+__device__ __forceinline__ void conv_tile(const ConvArgs& p, const TileSel& ts, const int m0, const int M, float (*As)[BK][BM],
+                                          float (*Bs)[BK][BN]) {
   constexpr int NA = BM * BK / 256;          // A floats per thread per slab (8 or 4)
   constexpr int NB = BK * BN / 256;          // B floats per thread per slab (8 or 4)
   constexpr int QM = TM / 4, QN = TN / 4;
@@ -49,7 +62,7 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const
   const int sp = blockIdx.z - g * p.splits;
   const int k_begin = sp * p.k_per_split;
   const int k_end = min(p.Kg, k_begin + p.k_per_split);
-  const int n0 = blockIdx.y * BN;
+  const int n0 = ts.n_tile * BN;
 
   // ---- A loader state: one output row per thread, NA consecutive k
   const int a_row = tid % BM;
@@ -57,7 +70,7 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const
   const int m = m0 + a_row;
   const bool a_valid = m < M;
   int an = 0, ih0 = 0, iw0 = 0;
-  if (a_valid && !p.gather) {
+  if (a_valid && !ts.gather) {
     int ow = m % d.OW;
     int t = m / d.OW;
     int oh = t % d.OH;
@@ -75,7 +88,7 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const
   const int b_k = tid / BTPR;                // rows covered per pass: 256 / BTPR
   constexpr int BPASS = BK / (256 / BTPR);
   static_assert(BPASS * 4 == NB, "B tiling");
-  const float* wg = p.w + g * p.Cout_g;
+  const float* wg = ts.w + g * p.Cout_g;
 
   float ra[NA];
   float rb[NB];
@@ -90,8 +103,8 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const
           const int tap = kg / p.Cin_g;
           const int c = kg - tap * p.Cin_g;
           const float* src = nullptr;
-          if (p.gather) {
-            const int r = p.gather[(long long)m * p.taps + tap];
+          if (ts.gather) {
+            const int r = ts.gather[(long long)m * p.taps + tap];
             if (r >= 0) src = xg + (long long)r * d.x_ld + c;
           } else {
             const int kh = tap / d.KW, kw = tap - kh * d.KW;
@@ -110,8 +123,8 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const
             if (k < k_end) {
               const int tap = k / p.Cin_g;
               const int c = k - tap * p.Cin_g;
-              if (p.gather) {
-                const int r = p.gather[(long long)m * p.taps + tap];
+              if (ts.gather) {
+                const int r = ts.gather[(long long)m * p.taps + tap];
                 if (r >= 0) e[i] = __ldg(xg + (long long)r * d.x_ld + c);
               } else {
                 const int kh = tap / d.KW, kw = tap - kh * d.KW;
@@ -225,8 +238,8 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const
     if (row >= M) continue;
     long long yoff, rpix = row, r1pix = row;
     int n = 0;
-    if (p.gather) {
-      yoff = (long long)(p.out_index ? p.out_index[row] : row) * d.y_ld;
+    if (ts.gather) {
+      yoff = (long long)(ts.out_index ? ts.out_index[row] : row) * d.y_ld;
     } else {
       const int ow = row % d.OW;
       const int t = row / d.OW;
@@ -249,7 +262,15 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const int m0, const
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = acc[i][q * 4 + j];
-      if (p.accumulate) {                                   // tap-major sparse conv: read-modify-write of a row this launch owns
+      if (p.accumulate == 2) {                              // fused tap-major sparse conv: taps race on a row -> red.add
+        if (vec_out) red_add_v4(yrow + col, v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (col + j < p.Cout_g) atomicAdd(yrow + col + j, v[j]);
+        }
+        continue;
+      }
+      if (p.accumulate) {                                   // read-modify-write of a row this launch owns
         if (vec_out) { const float4 t = *reinterpret_cast<const float4*>(yrow + col); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
         else {
 #pragma unroll
@@ -286,9 +307,45 @@ __global__ void __launch_bounds__(256) conv_igemm_simt(const ConvArgs p) {
   __shared__ __align__(16) float Bs[2][BK][BN];
   int M = p.M;
   if (p.m_count) M = min(M, *p.m_count);
+  const TileSel ts = {p.w, p.gather, p.out_index, (int)blockIdx.y};
   for (int mt = blockIdx.x; mt * BM < M; mt += gridDim.x) {
-    conv_tile<BM, BN, TM, TN, VECA, VECB>(p, mt * BM, M, As, Bs);
+    conv_tile<BM, BN, TM, TN, VECA, VECB>(p, ts, mt * BM, M, As, Bs);
     __syncthreads();                           // the next tile reuses the shared-memory slabs
+  }
+}
+
+// Fused tap-major sparse convolution: ONE launch walks every (tap, 64-pair tile, 64-column tile) work item of a layer.
+// The per-tap launches it replaces were latency-bound (a few 64-row tiles each, K <= 128) and serialised by the stream;
+// here all taps' tiles are in flight together and accumulate into the bias-initialised output rows with red.add.
+constexpr int MAX_KVOL = 32;
+template <bool VECA, bool VECB>
+__global__ void __launch_bounds__(256) sparse_conv_taps_kernel(const ConvArgs p, const int* __restrict__ pairs_in,
+                                                               const int* __restrict__ pairs_out,
+                                                               const int* __restrict__ pair_count, int kvol, int pair_cap) {
+  __shared__ __align__(16) float As[2][BK][64];
+  __shared__ __align__(16) float Bs[2][BK][64];
+  __shared__ int first[MAX_KVOL + 1], cnt[MAX_KVOL];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int t = 0; t < kvol; ++t) {
+      const int c = min(pair_count[t], pair_cap);
+      cnt[t] = c;
+      first[t] = acc;
+      acc += (c + 63) / 64;
+    }
+    first[kvol] = acc;
+  }
+  __syncthreads();
+  const int n_tiles = (p.Cout_g + 63) / 64;
+  const int total = first[kvol] * n_tiles;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int mt_all = item / n_tiles;
+    int tap = 0;
+    while (first[tap + 1] <= mt_all) ++tap;
+    const TileSel ts = {p.w + (long long)tap * p.Cin_g * p.d.Cout, pairs_in + (long long)tap * pair_cap,
+                        pairs_out + (long long)tap * pair_cap, item - mt_all * n_tiles};
+    conv_tile<64, 64, 4, 4, VECA, VECB>(p, ts, (mt_all - first[tap]) * 64, cnt[tap], As, Bs);
+    __syncthreads();
   }
 }
 
@@ -400,8 +457,9 @@ int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const 
 // ------------------------------------------------------------------------------------------------------------------
 // Tap-major sparse convolution (spconv SubMConv3d / SparseConv3d): the rulebook lists, per kernel tap, the (input row,
 // output row) pairs that exist.  One gather-GEMM launch per tap over just those pairs — instead of a 27-tap dense
-// gather where ~3 taps are populated — accumulating into the output rows (distinct within a tap, taps are stream-
-// ordered, so no atomics and a fixed summation order).  out = act(sum_taps W_tap . in[pair] + bias + res).
+// gather where ~3 taps are populated.  All taps of a layer run in one launch (sparse_conv_taps_kernel) and accumulate
+// into the bias-initialised output rows with red.add.f32 (summation order across taps is not fixed: results repeat to
+// fp32 rounding, not bitwise).  out = act(sum_taps W_tap . in[pair] + bias + res).
 namespace {
 __global__ void sparse_rows_init_kernel(float* __restrict__ y, int ld, const float* __restrict__ bias, int C,
                                         const int* __restrict__ count, int cap) {
@@ -446,12 +504,16 @@ extern "C" int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_i
   const bool veca = (d->Cin % 4 == 0) && (d->in_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats_in) & 15) == 0);
   const bool vecb = (d->Cout % 4 == 0) && (d->out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(feats_out) & 15) == 0);
-  for (int tap = 0; tap < d->kvol; ++tap) {
-    a.w = w + (long long)tap * d->Cin * d->Cout;
-    a.gather = pairs_in + (long long)tap * d->pair_cap;
-    a.out_index = pairs_out + (long long)tap * d->pair_cap;
-    a.m_count = pair_count + tap;
-    launch_cfg<64, 64, 4, 4>(a, veca, vecb, st);
+  TT_REQUIRE(d->kvol <= MAX_KVOL, "tt_sparse_conv", "kernel volume above 32 taps");
+  a.w = w;
+  a.accumulate = 2;
+  {
+    const long long cap_tiles = (long long)d->kvol * tt_cdiv(d->pair_cap, 64) * tt_cdiv(d->Cout, 64);
+    const int grid = (int)(cap_tiles < 148 * 6 ? cap_tiles : 148 * 6);
+    if (veca && vecb) sparse_conv_taps_kernel<true, true><<<grid, 256, 0, st>>>(a, pairs_in, pairs_out, pair_count, d->kvol, d->pair_cap);
+    else if (veca) sparse_conv_taps_kernel<true, false><<<grid, 256, 0, st>>>(a, pairs_in, pairs_out, pair_count, d->kvol, d->pair_cap);
+    else if (vecb) sparse_conv_taps_kernel<false, true><<<grid, 256, 0, st>>>(a, pairs_in, pairs_out, pair_count, d->kvol, d->pair_cap);
+    else sparse_conv_taps_kernel<false, false><<<grid, 256, 0, st>>>(a, pairs_in, pairs_out, pair_count, d->kvol, d->pair_cap);
     ++g_tt_launches;
   }
   TT_CHECK_LAUNCH("tt_sparse_conv(taps)");
