@@ -136,6 +136,7 @@ def main():
     ap.add_argument('--dump-convs', default=None, help='write per-conv-launch (name, flops, ms) of one step to this JSON file')
     ap.add_argument('--conv', default='3xtf32', choices=['simt', '3xtf32', 'tf32'],
                     help='dense-conv engine: tcgen05 3xTF32 (fp32-class, default), tcgen05 single-pass TF32, or SIMT fp32')
+    ap.add_argument('--tc-reserve', type=int, default=0, help='experiment: SMs the persistent tcgen05 kernels leave free for the side branch')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -208,6 +209,8 @@ def main():
             dist.barrier()
         return float(ms.item())
 
+    if args.tc_reserve:
+        lib.load().tt_debug_set(args.tc_reserve << 8)
     n_eager = lib.launch_count()
     step(resident)                                               # eager step: allocates every buffer, counts launches
     torch.cuda.synchronize()
@@ -227,9 +230,12 @@ def main():
 
     # ---- roofline of the dominant kernel family (implicit-GEMM conv): per-launch CUDA events on the launching stream
     model.use_graph = False                                      # per-launch events need eager launches
-    model.eng.prof = []
+    model.eng.prof, model.eng.marks = [], []
     step(resident)
     torch.cuda.synchronize()
+    mk = model.eng.marks
+    segments = {mk[i][0]: round(mk[i - 1][1].elapsed_time(mk[i][1]), 3) for i in range(1, len(mk))}
+    model.eng.marks = None
     conv_ms = sum(a.elapsed_time(b) for (_, _, a, b) in model.eng.prof)
     conv_flops = sum(f for (_, f, _, _) in model.eng.prof)
     n_conv = len(model.eng.prof)
@@ -253,7 +259,8 @@ def main():
                           'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
                           'traffic': None, 'peak_source': peak_src, 'launches_per_step': n_conv,
                           'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / (ms / args.steps),
-                          'algorithmic_flops_per_step': conv_flops})
+                          'algorithmic_flops_per_step': conv_flops},
+                segments_ms_serial_eager=segments)
     line['config']['parallelism'] = f'dp{world} (frames sharded, one NCCL all_gather of pred_wp)'
     if not args.no_cpu_baseline and args.gpus == 1:
         fps, n, cores, note = cpu_oracle(2, budget_s=90.0)

@@ -196,13 +196,18 @@ int tt_sparse_rulebook(const tt_rulebook_desc* d, const int* in_coords, const in
                        int* out_count, int* nbr, int* pairs_in, int* pairs_out, int* pair_count, void* workspace,
                        tt_stream_t stream);
 /* Tap-major sparse convolution: out[o] = act(sum_tap w[tap] . in[i] + bias + res[o]) over the rulebook's pairs; one
- * gather-GEMM per tap (output rows of a tap are distinct, taps are stream-ordered: no atomics, fixed summation order).
- * w: [kvol][Cin][Cout] fp32 (BatchNorm folded), res: optional [cap_out][res_ld] (SparseBasicBlock identity). */
+ * launch walks every (tap, pair tile) and accumulates into the bias-initialised output rows with red.add.f32 (the
+ * summation order across taps is not fixed: results repeat to fp32 rounding, not bitwise).
+ * impl 0/1: SIMT fp32, w = [kvol][Cin][Cout] fp32 (BatchNorm folded).
+ * impl 2/3: tcgen05 TF32 / 3xTF32 gather-GEMM, w = [2][Cout][kvol][Cin] hi / lo planes (as tt_conv2d); needs
+ *           Cin, Cout >= 32 and % 4 == 0, in_ld / out_ld % 4 == 0, 16-byte aligned pointers, else TT_ERR_UNSUPPORTED.
+ * res: optional [cap_out][res_ld] (SparseBasicBlock identity). */
 typedef struct {
   int Cin, Cout, kvol;
   int in_ld, out_ld, res_ld;
   int cap_out, pair_cap;         /* pair lists are [kvol][pair_cap] */
   int act;
+  int impl;
 } tt_sparse_conv_desc;
 int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_in, const float* w, const float* bias,
                    const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,

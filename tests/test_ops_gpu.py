@@ -312,13 +312,18 @@ def test_voxelize_mean_matches_oracle(eng):
     assert err < 1e-6
 
 
-def test_sparse_conv_layers_match_oracle(eng):
+@pytest.mark.parametrize('Cin,Cout,density,impl', [(16, 32, 0.08, 1), (64, 128, 0.25, 3), (32, 32, 0.3, 3), (128, 64, 0.15, 3)])
+def test_sparse_conv_layers_match_oracle(Cin, Cout, density, impl):
+    """impl 1: fused SIMT gather GEMM; impl 3: tcgen05 3xTF32 gather GEMM (cp.async row gather, red.add epilogue)."""
     from oracle.lidar import SparseConvBase, SparseTensor
     from thinktwice_b200.lib import RulebookDesc, _p
     from thinktwice_b200 import lib
+    from thinktwice_b200.engine import Engine
+    from thinktwice_b200.weights import tf32_split
+    eng = Engine('cuda:0', impl=impl)
     gen = torch.Generator().manual_seed(13)
-    B, shape, Cin, Cout = 2, (9, 24, 20), 16, 32
-    mask = torch.rand(B, *shape, generator=gen) < 0.08
+    B, shape = 2, (9, 24, 20)
+    mask = torch.rand(B, *shape, generator=gen) < density
     coords = mask.nonzero().int()
     coords = coords[torch.randperm(coords.shape[0], generator=gen)]
     n = coords.shape[0]
@@ -351,11 +356,15 @@ def test_sparse_conv_layers_match_oracle(eng):
         assert int(pcount.sum()) == int((nbr[:int(ocount.item())] >= 0).sum())               # both rulebook forms agree
         w = conv.weight.detach()
         from thinktwice_b200.engine import PackedConv
-        pw = PackedConv(w.reshape(Cout, kvol, Cin).permute(1, 2, 0).reshape(kvol * Cin, Cout).contiguous().cuda(), None, Cin, Cout)
+        w_tc = torch.stack(tf32_split(w.reshape(Cout, kvol, Cin))).contiguous().cuda() if impl == 3 else None
+        pw = PackedConv(w.reshape(Cout, kvol, Cin).permute(1, 2, 0).reshape(kvol * Cin, Cout).contiguous().cuda(), None, Cin, Cout,
+                        w_tc=w_tc)
+        n0 = lib.launch_count()
         fin = torch.zeros(cap_in, Cin, device='cuda'); fin[:n] = feats.cuda()
         out = torch.zeros(cap_out, Cout, device='cuda')
         rule = dict(kvol=kvol, cap=cap_out, pairs_in=pin, pairs_out=pout, pair_count=pcount, count=ocount)
         eng.sparse_conv(fin, pw, rule, out)
+        assert lib.launch_count() - n0 == 3                        # init + ONE launch over all taps + finish
         m = int(ocount.item())
         D, H, W = out_shape
         dense = torch.zeros(B, H, W, Cout * D, device='cuda')

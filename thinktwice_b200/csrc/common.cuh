@@ -50,6 +50,11 @@ TT_DEVICE float tt_act(float v, int act) {
   return tt_act_slow(v, act);
 }
 
+// 16-byte vector reduction into global memory (sm_90+): the sparse convolutions accumulate taps into an output row
+TT_DEVICE void tt_red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 TT_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -42,10 +42,6 @@ struct TileSel {
   int n_tile;
 };
 
-TT_DEVICE void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 constexpr int BK = 16;
 
 template <int BM, int BN, int TM, int TN, bool VECA, bool VECB>
@@ -263,7 +259,7 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const TileSel& ts, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = acc[i][q * 4 + j];
       if (p.accumulate == 2) {                              // fused tap-major sparse conv: taps race on a row -> red.add
-        if (vec_out) red_add_v4(yrow + col, v[0], v[1], v[2], v[3]);
+        if (vec_out) tt_red_add_v4(yrow + col, v[0], v[1], v[2], v[3]);
         else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (col + j < p.Cout_g) atomicAdd(yrow + col + j, v[j]);
@@ -480,6 +476,10 @@ __global__ void sparse_rows_finish_kernel(float* __restrict__ y, int ld, const f
 }
 }  // namespace
 
+bool tt_sparse_conv_tc_supported(const tt_sparse_conv_desc* d, const void* x, const void* w, const void* y);
+int tt_sparse_conv_tc(const tt_sparse_conv_desc* d, const float* feats_in, const float* w_tc, const int* pairs_in,
+                      const int* pairs_out, const int* pair_count, float* feats_out, cudaStream_t st);
+
 extern "C" int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_in, const float* w, const float* bias,
                               const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,
                               const int* out_count, float* feats_out, tt_stream_t stream) {
@@ -505,6 +505,18 @@ extern "C" int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_i
   const bool vecb = (d->Cout % 4 == 0) && (d->out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(feats_out) & 15) == 0);
   TT_REQUIRE(d->kvol <= MAX_KVOL, "tt_sparse_conv", "kernel volume above 32 taps");
+  if (d->impl >= 2) {                                          // tcgen05 gather-GEMM; w = [2][Cout][kvol][Cin] hi / lo planes
+    if (!tt_sparse_conv_tc_supported(d, feats_in, w, feats_out)) {
+      tt_set_error("tt_sparse_conv: impl %d needs Cin, Cout >= 32 and multiples of 4, in_ld / out_ld multiples of 4, 16-byte aligned pointers", d->impl);
+      return TT_ERR_UNSUPPORTED;
+    }
+    const int rc = tt_sparse_conv_tc(d, feats_in, w, pairs_in, pairs_out, pair_count, feats_out, st);
+    if (rc != TT_OK) return rc;
+    sparse_rows_finish_kernel<<<nb, 256, 0, st>>>(feats_out, d->out_ld, res, d->res_ld, d->Cout, out_count, d->cap_out, d->act);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_sparse_conv(finish)");
+    return TT_OK;
+  }
   a.w = w;
   a.accumulate = 2;
   {

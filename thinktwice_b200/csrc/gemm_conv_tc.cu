@@ -22,6 +22,7 @@
 //     for transposed convs handled in the store address).
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -142,7 +143,15 @@ struct TcArgs {
   int total_pix;         // N * OH * OW
   int dbg;               // diagnosis knobs (tt_debug_set): 1 = no epilogue global traffic, 2 = no A loads, 4 = no MMAs
   int m_tiles, n_tiles;  // persistent tile walk: tile t -> (m tile t / n_tiles, n tile t % n_tiles)
+  // GATHER (tap-major sparse convolution): GEMM rows are the (input row, output row) pairs of one kernel tap
+  const float* gx;       // feature rows [.][gx_ld]
+  int gx_ld;
+  const int* pairs_in;   // [kvol][pair_cap]
+  const int* pairs_out;  // [kvol][pair_cap]
+  const int* pair_count; // [kvol]
+  int kvol, pair_cap;
 };
+constexpr int MAX_KVOL = 32;
 
 // operand split used by the in-kernel split warps: hi = x rounded to nearest TF32 (ties away: one IADD + one LOP3 on
 // the alu pipe), lo = x - hi (exact in fp32, one FADD on the fma pipe).  |lo| <= 2^-11 |x| with either sign, so the
@@ -156,6 +165,12 @@ TT_DEVICE float4 lds128(uint32_t a) {
 TT_DEVICE void sts128(uint32_t a, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+TT_DEVICE void cp_async16(uint32_t dst, const void* src, int src_bytes) {      // src_bytes 0: zero-fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+TT_DEVICE void cp_async_arrive_noinc(uint64_t* bar) {                          // arrives once this thread's cp.asyncs landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 TT_DEVICE void split_rn(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
@@ -168,7 +183,11 @@ TT_DEVICE void split_rn(float x, float& hi, float& lo) {
 // Persistent, warp-specialised kernel: each CTA pair walks tile pairs pt = blockIdx.x / 2, += gridDim.x / 2.  The smem
 // ring, the TMEM ping-pong and all phase counters run ACROSS tiles, so while the epilogue warps store tile i the
 // TMA and MMA warps are already deep into tile i + 1.
-template <int BN, int STAGES, bool MERGED>
+// GATHER = true turns the kernel into the tap-major sparse convolution (spconv SubMConv3d / SparseConv3d): work items
+// are (tap, pair-tile pair, N tile); warp 0 gathers the activation rows of a tile with 16-byte cp.async (zero-fill for
+// the tile tail / channel tail) straight into the 128-byte-swizzled stage buffer, signalling the same `full` barrier
+// the weight TMA uses; the epilogue accumulates into the bias-initialised output rows with red.add.v4.f32.
+template <int BN, int STAGES, bool MERGED, bool GATHER>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
@@ -196,6 +215,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* acc_full = bars + 3 * STAGES;                 // [2]       MMA -> epilogue (chunk finished)
   uint64_t* acc_empty = bars + 3 * STAGES + 2;            // [2]       epilogue -> MMA (accumulators drained)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  int* sp_first = reinterpret_cast<int*>(tmem_slot + 2);   // GATHER: [kvol + 1] first tile pair of each tap
+  int* sp_cnt = sp_first + MAX_KVOL + 1;                  // GATHER: [kvol] pairs of each tap
 
   const tt_conv_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,14 +224,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int k_iters = taps * p.n_slabs;
   const int n_chunks = (k_iters + p.chunk - 1) / p.chunk;
   const uint32_t rank = cluster_ctarank();                // 0 / 1 inside the CTA pair
-  const int m_pairs = (p.m_tiles + 1) / 2;
-  const int total_pairs = m_pairs * p.n_tiles;              // both CTAs iterate the same pair list (lockstep)
   const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); mbar_init(&conv[s], 2); }   // empty: both MMA threads of the pair; conv: 2 split warps
+    // full: the producer's expect_tx arrival (+ 32 cp.async arrivals in GATHER mode); empty: both MMA threads of the pair;
+    // conv: 2 split warps
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], 2); mbar_init(&conv[s], 2); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }   // 8 epilogue warps arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (GATHER && threadIdx.x == 64) {                        // tile-pair prefix over the taps (identical in both CTAs)
+    int acc = 0;
+    for (int t = 0; t < p.kvol; ++t) {
+      const int c = min(p.pair_count[t], p.pair_cap);
+      sp_cnt[t] = c;
+      sp_first[t] = acc;
+      acc += ((c + BM - 1) / BM + 1) / 2;
+    }
+    sp_first[p.kvol] = acc;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
@@ -221,8 +252,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   cluster_sync_all();                                       // the peer's barriers are initialised before any multicast lands
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // both CTAs iterate the same pair list (lockstep)
+  const int total_pairs = GATHER ? sp_first[p.kvol] * p.n_tiles : ((p.m_tiles + 1) / 2) * p.n_tiles;
+  // work item -> (N tile, M tile of this CTA, tap, rows of that tap)
+  auto decode = [&](int pt, int& nt, int& mt, int& tap, int& count) {
+    nt = pt % p.n_tiles;
+    const int pm = pt / p.n_tiles;
+    tap = 0; count = 0;
+    if (GATHER) {
+      while (sp_first[tap + 1] <= pm) ++tap;
+      mt = 2 * (pm - sp_first[tap]) + (int)rank;
+      count = sp_cnt[tap];
+    } else {
+      mt = 2 * pm + (int)rank;
+    }
+  };
 
-  if (warp == 0) {
+  if (warp == 0 && GATHER) {
+    // ===================================================================== gather producer (whole warp) + weight TMA
+    const uint32_t txb = (p.terms == 3 ? 2 : 1) * B_BYTES;
+    int ig = 0;
+    for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+      int nt, mt, tap, count;
+      decode(pt, nt, mt, tap, count);
+      const int n0 = nt * BN;
+      const int* pin = p.pairs_in + (long long)tap * p.pair_cap;
+      int rows[4];                                            // this lane's rows: lane, lane + 32, lane + 64, lane + 96
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = mt * BM + lane + 32 * i;
+        rows[i] = m < count ? __ldg(pin + m) : -1;
+      }
+      for (int it = 0; it < k_iters; ++it, ++ig) {
+        const int s = ig % STAGES;
+        mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        if (lane == 0) {
+          mbar_expect_tx(&full[s], txb);
+          tma_load_3d_mc(st + 2 * A_BYTES + rank * (B_BYTES / 2), &map_b_hi, &full[s], it * KS, tap, n0 + (int)rank * (BN / 2), 3);
+          if (p.terms == 3)
+            tma_load_3d_mc(st + 2 * A_BYTES + B_BYTES + rank * (B_BYTES / 2), &map_b_lo, &full[s], it * KS, tap, n0 + (int)rank * (BN / 2), 3);
+        }
+        const int c0 = it * KS;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = lane + 32 * i;
+          const float* src = p.gx + (long long)max(rows[i], 0) * p.gx_ld + c0;
+          const uint32_t dst = smem_u32(st) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {                       // 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+            const bool ok = rows[i] >= 0 && c0 + j * 4 < d.Cin;
+            cp_async16(dst + ((j ^ (r & 7)) << 4), ok ? src + j * 4 : p.gx, ok ? 16 : 0);
+          }
+        }
+        cp_async_arrive_noinc(&full[s]);
+      }
+    }
+  } else if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KS * 4;   // bytes one activation box delivers
@@ -334,11 +420,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* tile = tile_all + (warp - 2) * 32 * PITCH;      // warp-private transposition buffer [32 rows][PITCH]
     int cg = 0;
     for (int pt = pair0; pt < total_pairs; pt += pair_step) {
-      const int nt = pt % p.n_tiles, mt = 2 * (pt / p.n_tiles) + (int)rank;
-      const bool real_tile = mt < p.m_tiles;
+      int nt, mt, tap, count;
+      decode(pt, nt, mt, tap, count);
+      const bool real_tile = GATHER ? mt * BM < count : mt < p.m_tiles;
       const int n0 = nt * BN + half * HN;
       // ---- this thread's row -> output / residual addresses (once per tile); prefetch the residual lines into L2
-      {
+      if (GATHER) {
+        const int m = mt * BM + r;
+        const bool valid = m < count;
+        if (half == 0) {
+          const int orow = valid ? __ldg(p.pairs_out + (long long)tap * p.pair_cap + m) : 0;
+          row_y[r] = (long long)orow * d.y_ld + d.y_coff;
+          row_r1[r] = 0;
+          row_r2[r] = 0;
+          row_flag[r] = valid ? 1 : 0;
+        }
+      } else {
         bool valid;
         int nimg, oh, ow;
         long long rrow;
@@ -441,9 +538,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const float4 o = make_float4(acc4[i].x + bv.x + ra[i].x + rb[i].x, acc4[i].y + bv.y + ra[i].y + rb[i].y,
                                          acc4[i].z + bv.z + ra[i].z + rb[i].z, acc4[i].w + bv.w + ra[i].w + rb[i].w);
             float* dst = p.y + ((p.dbg & 8) ? (long long)(threadIdx.x * 4) : yo[i] + col);   // dbg 8: all stores hit one hot 2 KB
-            if (!(p.dbg & 16) || o.x == 12345.678f)                                          // dbg 16: no store at all
+            if (GATHER) {                                      // taps race on an output row: accumulate with red.add
+              tt_red_add_v4(dst, o.x, o.y, o.z, o.w);
+            } else if (!(p.dbg & 16) || o.x == 12345.678f) {                                 // dbg 16: no store at all
               *reinterpret_cast<float4*>(dst) =
                   make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
+            }
           }
         }
       }
@@ -569,13 +669,13 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     if (!encode_map(&mb_hi, w_tc, 3, dims, str, box)) return TT_ERR_CUDA;
     if (!encode_map(&mb_lo, w_tc + wplane, 3, dims, str, box)) return TT_ERR_CUDA;
   }
-  a.dbg = g_tt_debug;
+  a.dbg = g_tt_debug & 0xFF;
   a.m_tiles = grid_x;
   a.n_tiles = tt_cdiv(d->Cout, BN);
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   const long long pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles;
-  const long long max_pairs = num_sms / 2;
+  const long long max_pairs = (num_sms - ((g_tt_debug >> 8) & 0xFF)) / 2;        // debug bits 8..15: SMs left to a concurrent branch
   dim3 grid((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));  // persistent CTA pairs (cluster of 2), one CTA per SM
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -586,30 +686,101 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 256;  // 8 warp-private slabs + row tables + barriers (13 x 8 B)
+  constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;  // 8 warp-private slabs + row tables + barriers (13 x 8 B) + tap prefix
   cudaError_t lerr;
   if (BN == 256) {
     a.chunk = 2;
     constexpr int smem = 2 * (2 * BM * KS * 4 + 2 * 256 * KS * 4) + 1024 + EPI_BYTES;
     static bool set256 = false;
-    if (!set256) { cudaFuncSetAttribute(conv_tc_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set256 = true; }
+    if (!set256) { cudaFuncSetAttribute(conv_tc_kernel<256, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set256 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, 2, true>, ma, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, 2, true, false>, ma, mb_hi, mb_lo, a);
   } else if (BN == 128) {
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;
-    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
+    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false>, ma, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false, false>, ma, mb_hi, mb_lo, a);
   } else {
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
     static bool set64 = false;
-    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
+    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false>, ma, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false, false>, ma, mb_hi, mb_lo, a);
   }
   if (lerr != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_conv2d(tc)");
+  return TT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tap-major sparse convolution on the tensor cores (GATHER mode of the kernel above).  The caller (tt_sparse_conv) has
+// initialised the output rows with the bias and applies residual + activation afterwards.
+bool tt_sparse_conv_tc_supported(const tt_sparse_conv_desc* d, const void* x, const void* w, const void* y) {
+  if (d->Cin % 4 || d->Cout % 4 || d->in_ld % 4 || d->out_ld % 4 || d->Cin < 32 || d->Cout < 32 || d->kvol > MAX_KVOL) return false;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return false;
+  return true;
+}
+
+int tt_sparse_conv_tc(const tt_sparse_conv_desc* d, const float* feats_in, const float* w_tc, const int* pairs_in,
+                      const int* pairs_out, const int* pair_count, float* feats_out, cudaStream_t st) {
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d.N = a.d.H = a.d.W = a.d.OH = a.d.OW = a.d.yH = a.d.yW = 1;
+  a.d.KH = a.d.KW = a.d.stride = a.d.dil = a.d.groups = 1;
+  a.d.oy_mul = a.d.ox_mul = 1;
+  a.d.Cin = d->Cin; a.d.x_ld = d->in_ld; a.d.Cout = d->Cout; a.d.y_ld = d->out_ld;
+  a.d.act = TT_ACT_NONE;
+  a.y = feats_out;
+  a.terms = d->impl == 3 ? 3 : 1;
+  a.chunk = a.terms == 3 ? 4 : 16;
+  a.n_slabs = (d->Cin + KS - 1) / KS;
+  a.dbg = g_tt_debug & 0xFF;
+  a.gx = feats_in; a.gx_ld = d->in_ld;
+  a.pairs_in = pairs_in; a.pairs_out = pairs_out; a.pair_count = pair_count;
+  a.kvol = d->kvol; a.pair_cap = d->pair_cap;
+  const int BN = d->Cout > 64 ? 128 : 64;
+  a.n_tiles = tt_cdiv(d->Cout, BN);
+  CUtensorMap mb_hi, mb_lo;
+  {
+    const size_t wplane = (size_t)d->Cout * d->kvol * d->Cin;
+    cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->kvol, (cuuint64_t)d->Cout};
+    cuuint64_t str[2] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)d->kvol * d->Cin * 4};
+    cuuint32_t box[3] = {KS, 1, (cuuint32_t)(BN / 2)};
+    if (!encode_map(&mb_hi, w_tc, 3, dims, str, box)) return TT_ERR_CUDA;
+    if (!encode_map(&mb_lo, w_tc + wplane, 3, dims, str, box)) return TT_ERR_CUDA;
+  }
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const long long cap_pairs = (long long)d->kvol * ((tt_cdiv(d->pair_cap, BM) + 1) / 2) * a.n_tiles;
+  const long long max_pairs = num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (cap_pairs < max_pairs ? cap_pairs : max_pairs)));
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;
+  cudaError_t lerr;
+  if (BN == 128) {
+    constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
+    static bool set128 = false;
+    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
+    cfg.dynamicSmemBytes = smem;
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false, true>, mb_hi, mb_hi, mb_lo, a);
+  } else {
+    constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
+    static bool set64 = false;
+    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
+    cfg.dynamicSmemBytes = smem;
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false, true>, mb_hi, mb_hi, mb_lo, a);
+  }
+  if (lerr != cudaSuccess) { tt_set_error("tt_sparse_conv(tc): cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_sparse_conv(tc)");
   return TT_OK;
 }

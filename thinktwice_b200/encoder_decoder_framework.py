@@ -150,14 +150,23 @@ class EncoderDecoder(nn.Module):
     def _device_forward(self):
         """Device half: extract_sensor_feat (framework:238-250) + get_fusion_feat + decoder, kernels only."""
         e = self.eng
+        # the LiDAR encoder (small, latency-bound sparse kernels) runs on a side stream beside the camera encoder
+        # (large tensor-core kernels): the two branches only meet in get_fusion_feat
+        e.mark('start')
+        with e.side_branch() as side:
+            lidar = self.lidar_encoder(e.static('in.points'))
+        e.mark('lidar_encoder')
         cam = self.img_encoder.forward_device(e.static('in.img'))
         cam['bev'] = e.anti_transpose(cam['bev'], 'cam.bev.at')     # rot90(flip): match the Roach BEV
         st = e.static('in.state')
         m = e.linear(e.wrap(st.view(-1, 1, 1, 12)), self.w['meas0'], name='meas.h', act=ACT_RELU)
         meas = e.linear(m, self.w['meas2'], name='meas', act=ACT_RELU)
-        lidar = self.lidar_encoder(e.static('in.points'))
+        side.join()
+        e.mark('camera_encoder')
         flat, bev32, mid, lidar_hi = self.get_fusion_feat(cam['bev'], lidar[0])
+        e.mark('bev_fusion')
         pred = self.decoder(flat, bev32, meas, None, self, None, [None, None, cam['fpn_feats'], lidar_hi])
+        e.mark('decoder')
         self.last_cam_feat = cam                                   # cam['seg'] etc. for parity checks
         return pred
 

@@ -50,16 +50,71 @@ class PackedConv:
         self.w_tc = w_tc            # [2][Cout][taps][Cin] TF32 hi / lo planes for the tcgen05 path (or None)
 
 
+class _SideBranch:
+    def __init__(self, eng):
+        self.eng = eng
+
+    def __enter__(self):
+        e = self.eng
+        # serial when profiling per-launch events (overlapped kernels would inflate each other's timings) or off-GPU
+        self.active = e.overlap and e.prof is None and e.device.type == 'cuda' and torch.cuda.is_available()
+        if not self.active:
+            return self
+        if e._side is None:
+            e._side = torch.cuda.Stream(device=e.device)
+        self.main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(self.main)
+        e._side.wait_event(fork)
+        self.ctx = torch.cuda.stream(e._side)
+        self.ctx.__enter__()
+        e.lane = 1
+        return self
+
+    def __exit__(self, *exc):
+        e = self.eng
+        if not self.active:
+            return False
+        e.lane = 0
+        self.done = torch.cuda.Event()
+        self.done.record(e._side)
+        self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        """make the current (main) stream wait for the side branch."""
+        if self.active:
+            torch.cuda.current_stream().wait_event(self.done)
+
+
 class Engine:
     def __init__(self, device, impl=lib.IMPL_AUTO):
         self.device = torch.device(device)
         self.impl = impl
         self.bufs = {}
-        self.tc_ws = None           # grow-only conv workspace (split-K partial sums of the SIMT kernel)
+        self.tc_ws = {}             # per lane: grow-only conv workspace (split-K partial sums of the SIMT kernel)
+        self.lane = 0               # 0 = main stream; 1 = side stream (independent branch running concurrently)
+        self._side = None
+        self.overlap = True         # run independent branches (side_branch) concurrently
+        self.marks = None           # bench.py: list of (segment name, event) recorded by mark() in a serial eager step
         self.tc_min_rows = 512
         self.tc_strides = (1, 2)
         self.prof = None            # bench.py: list of (name, flops, start_event, end_event) per conv launch
         lib.load()
+
+    def mark(self, name):
+        """segment boundary for bench.py's per-segment timing (no-op unless `marks` is a list)."""
+        if self.marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    # ------------------------------------------------------------------ streams
+    def side_branch(self):
+        """context manager: kernels issued inside run on a side stream forked from the current one (an independent
+        branch of the forward, e.g. the LiDAR encoder beside the camera encoder); `join()` on exit.  Works eagerly and
+        under CUDA-graph capture (fork / join become graph dependencies)."""
+        return _SideBranch(self)
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name, shape, dtype=torch.float32, zero=False):
@@ -133,9 +188,9 @@ class Engine:
         ws = None
         need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # SIMT: split-K partials; tcgen05: 0
         if need:
-            if self.tc_ws is None or self.tc_ws.numel() < need:
-                self.tc_ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
-            ws = self.tc_ws
+            ws = self.tc_ws.get(self.lane)
+            if ws is None or ws.numel() < need:
+                ws = self.tc_ws[self.lane] = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -164,10 +219,13 @@ class Engine:
         d.Cin, d.Cout, d.kvol = pw.Cin, pw.Cout, rule['kvol']
         d.in_ld, d.out_ld, d.res_ld = feats.shape[1], out.shape[1], (res.shape[1] if res is not None else 0)
         d.cap_out, d.pair_cap, d.act = rule['cap'], rule['cap'], act
+        use_tc = (self.impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and pw.Cin >= 32 and pw.Cout >= 32
+                  and pw.Cin % 4 == 0 and d.in_ld % 4 == 0 and d.out_ld % 4 == 0 and rule['kvol'] <= 32)
+        d.impl = self.impl if use_tc else lib.IMPL_SIMT
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        lib.check(lib.load().tt_sparse_conv(C.byref(d), _p(feats), _p(pw.w), _p(pw.bias), _p(res), _p(rule['pairs_in']),
+        lib.check(lib.load().tt_sparse_conv(C.byref(d), _p(feats), _p(pw.w_tc if use_tc else pw.w), _p(pw.bias), _p(res), _p(rule['pairs_in']),
                                             _p(rule['pairs_out']), _p(rule['pair_count']), _p(rule['count']), _p(out),
                                             _stream()), f'tt_sparse_conv[{name}]')
         if self.prof is not None:

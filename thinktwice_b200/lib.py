@@ -49,7 +49,7 @@ class RulebookDesc(C.Structure):
 
 
 class SparseConvDesc(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ('Cin', 'Cout', 'kvol', 'in_ld', 'out_ld', 'res_ld', 'cap_out', 'pair_cap', 'act')]
+    _fields_ = [(n, C.c_int) for n in ('Cin', 'Cout', 'kvol', 'in_ld', 'out_ld', 'res_ld', 'cap_out', 'pair_cap', 'act', 'impl')]
 
 
 class LookDesc(C.Structure):

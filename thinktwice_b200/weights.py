@@ -124,7 +124,7 @@ class Packer:
         w = w * s.view(-1, 1, 1, 1, 1)
         Cout, kd, kh, kw, Cin = w.shape
         packed = w.reshape(Cout, kd * kh * kw, Cin).permute(1, 2, 0).reshape(kd * kh * kw * Cin, Cout)
-        pc = PackedConv(self._dev(packed), self._dev(t), Cin, Cout)
+        pc = PackedConv(self._dev(packed), self._dev(t), Cin, Cout, w_tc=self._tc(w.reshape(Cout, kd * kh * kw, Cin)) if Cin >= 32 else None)
         return pc, (kd, kh, kw)
 
     def vec(self, n):
