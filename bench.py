@@ -136,6 +136,7 @@ def main():
     ap.add_argument('--dump-convs', default=None, help='write per-conv-launch (name, flops, ms) of one step to this JSON file')
     ap.add_argument('--conv', default='3xtf32', choices=['simt', '3xtf32', 'tf32'],
                     help='dense-conv engine: tcgen05 3xTF32 (fp32-class, default), tcgen05 single-pass TF32, or SIMT fp32')
+    ap.add_argument('--dbg', type=int, default=0, help='experiment: tt_debug_set knob bits (see csrc/gemm_conv_tc.cu)')
     ap.add_argument('--tc-reserve', type=int, default=0, help='experiment: SMs the persistent tcgen05 kernels leave free for the side branch')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
@@ -209,8 +210,8 @@ def main():
             dist.barrier()
         return float(ms.item())
 
-    if args.tc_reserve:
-        lib.load().tt_debug_set(args.tc_reserve << 8)
+    if args.tc_reserve or args.dbg:
+        lib.load().tt_debug_set((args.tc_reserve << 8) | args.dbg)
     n_eager = lib.launch_count()
     step(resident)                                               # eager step: allocates every buffer, counts launches
     torch.cuda.synchronize()

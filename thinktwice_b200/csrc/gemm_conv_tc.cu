@@ -344,6 +344,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc2 = make_idesc(BM, MERGED ? BN : 2 * BN);   // hi*hi | hi*lo in one instruction
       int ig = 0, cg = 0;                                                       // ring / chunk counters across tiles
       for (int pt = pair0; pt < total_pairs; pt += pair_step) {
         int it = 0;
@@ -365,10 +366,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (p.dbg & 4) break;
               const uint32_t off = kk * 32;
               const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-              umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
-              if (p.terms == 3) {
-                umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, MERGED ? 1u : acc);
+              if (p.terms == 3 && !MERGED && !(p.dbg & 32)) {
+                // A_hi x [B_hi ; B_lo] as ONE N = 2 BN instruction: the lo weight tile follows the hi tile in shared
+                // memory and the correction accumulator follows the main one in TMEM, so hi*hi and hi*lo share a
+                // single read of the A_hi slab (the tf32 SS-MMA rate is shared-memory-read bound).
+                umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc2, acc);
                 umma_tf32(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
+              } else {
+                umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
+                if (p.terms == 3) {
+                  umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, 1u);
+                  umma_tf32(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
+                }
               }
             }
             first = false;

@@ -80,10 +80,8 @@ class LSS:
         w['aspp'] = [pk.conv(f'{a}aspp{i + 1}.atrous_conv', bn=f'{a}aspp{i + 1}.bn') for i in range(4)]
         w['aspp_gap'] = pk.conv(a + 'global_avg_pool.1', bn=a + 'global_avg_pool.2')
         w['aspp_out'] = pk.conv(a + 'conv1', bn=a + 'bn1')
-        w['dcn_off'] = pk.conv(d + 'depth_conv.4.conv_offset')
-        dcn = pk.conv(d + 'depth_conv.4', groups=4)
-        dcn.Cin, dcn.KH, dcn.KW = 9 * self.mid, 1, 1                  # GEMM over the sampled columns
-        w['dcn'] = dcn
+        w['dcn_off'] = pk.conv(d + 'depth_conv.4.conv_offset', cout_pad=32)   # 18 -> 32 channels: tcgen05 instead of SIMT
+        w['dcn'] = pk.conv_group_gemms(d + 'depth_conv.4', groups=4)   # one GEMM per group over the sampled columns
         w['depth_out'] = pk.conv(d + 'depth_conv.5')
         u = p + 'seg_net.'
         for l in (4, 3, 2):
@@ -188,7 +186,11 @@ class LSS:
         off = e.conv(y, w['dcn_off'], name='dn.dcn.off', pad=1)
         col = e.fmap('dn.dcn.col', BN, H, W, 9 * self.mid)
         lib.call('tt_dcn_im2col', _p(y.t), _p(off.t), off.ld, _p(col.t), BN, H, W, self.mid, 4)
-        y = e.conv(col, w['dcn'], name='dn.dcn.out')
+        yd = e.fmap('dn.dcn.out', BN, H, W, self.mid)
+        cg = 9 * self.mid // len(w['dcn'])
+        for g, wg in enumerate(w['dcn']):                               # grouped conv = one dense GEMM per group slice
+            e.conv(col.slice(g * cg, cg), wg, out=yd.slice(g * wg.Cout, wg.Cout), name='dn.dcn.out')
+        y = yd
         return e.conv(y, w['depth_out'], name='dn.depth')
 
     def _upcat(self, x, skip, ups, name):

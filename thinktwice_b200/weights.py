@@ -55,7 +55,7 @@ class Packer:
         out[:, ok] = w[:, idx[ok]]
         return out
 
-    def conv(self, n, bn=None, eps=1e-5, groups=1, cin_pad=None, cin_index=None):
+    def conv(self, n, bn=None, eps=1e-5, groups=1, cin_pad=None, cin_index=None, cout_pad=None):
         """Conv2d weight (Cout, Cin_g, KH, KW) [+bias] followed by BN `bn` -> PackedConv."""
         w = self.sd[n + '.weight'].double()
         b = self.sd.get(n + '.bias')
@@ -66,6 +66,10 @@ class Packer:
             b = t if b is None else b * s + t
         if cin_index is not None:
             w = self._reindex(w, cin_index)
+        if cout_pad is not None and cout_pad > w.shape[0]:           # zero output channels: lifts a thin conv onto the tensor cores
+            w = torch.cat([w, w.new_zeros((cout_pad - w.shape[0],) + tuple(w.shape[1:]))], 0)
+            if b is not None:
+                b = torch.cat([b, b.new_zeros(cout_pad - b.shape[0])])
         Cout, Cg, KH, KW = w.shape
         if cin_pad is not None and cin_pad > Cg:
             assert groups == 1
@@ -74,6 +78,19 @@ class Packer:
         packed = w.permute(2, 3, 1, 0).reshape(KH * KW * Cg, Cout)
         w_tc = self._tc(w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cg)) if groups == 1 else None
         return PackedConv(self._dev(packed), self._dev(b), Cg * groups, Cout, KH, KW, groups, w_tc)
+
+    def conv_group_gemms(self, n, groups):
+        """grouped Conv2d weight (Cout, Cin_g, KH, KW) -> one dense GEMM per group over im2col columns laid out
+        [group][tap][Cin_g] (tt_dcn_im2col): list of PackedConv with Cin = KH*KW*Cin_g, Cout = Cout/groups."""
+        w = self.sd[n + '.weight'].double()
+        assert self.sd.get(n + '.bias') is None
+        Cout, Cg, KH, KW = w.shape
+        Co = Cout // groups
+        out = []
+        for g in range(groups):
+            wg = w[g * Co:(g + 1) * Co].permute(0, 2, 3, 1).reshape(Co, KH * KW * Cg)      # K = (tap, cin)
+            out.append(PackedConv(self._dev(wg.t()), None, KH * KW * Cg, Co, w_tc=self._tc(wg.reshape(Co, 1, KH * KW * Cg))))
+        return out
 
     def linear(self, n, bn_after=None, eps=1e-5, in_affine=None, cin_pad=None, weight=None, bias=None, cin_index=None):
         """Linear (Cout, Cin).  in_affine=(s, t): the input is s*x + t (a folded BatchNorm1d in front);
