@@ -103,6 +103,9 @@ int tt_lift_splat(const tt_lift_splat_desc* d, const float* depth_logits, const 
 typedef struct {
   int N, H, W, Cin, x_ld, x_coff;
   long long x_nstride, y_nstride;  /* floats between consecutive images; 0 = dense (H*W*x_ld, yH*yW*y_ld) */
+  long long x_hstride;             /* floats between consecutive input rows; 0 = dense (W*x_ld).  With x_ld < Cin the
+                                    * "channels" of a pixel run on into the next pixels of the row: a KW-wide tap row
+                                    * of a thin-channel conv becomes ONE K slab (row-packed stem conv, see lss.py) */
   int Cout, KH, KW, stride, pad, dil, groups;
   int OH, OW;
   int y_ld, y_coff, yH, yW, oy_mul, oy_add, ox_mul, ox_add;
@@ -123,6 +126,10 @@ int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float
  * (3) memory-bound helpers (torch elementwise / pooling / interpolation ops)
  */
 /* NCHW fp32 -> channels-last with `ld` floats per pixel (channels >= C are zero-filled up to cpad) */
+/* same, into a larger [N][out_H][out_W][y_ld] buffer at pixel offset (top, left): physical zero padding for
+ * row-packed convolutions (the border is never written: zero it once). */
+int tt_nchw_to_nhwc_padded(const float* x, float* y, int N, int C, int H, int W, int y_ld, int cpad, int out_H,
+                           int out_W, int top, int left, tt_stream_t stream);
 int tt_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, int y_ld, int y_coff, int cpad,
                     tt_stream_t stream);
 int tt_nhwc_to_nchw(const float* x, int x_ld, int x_coff, float* y, int N, int C, int H, int W, tt_stream_t stream);

@@ -100,3 +100,29 @@ def test_tc_conv_epilogue_offsets_residuals_scatter():
         for j in range(2):
             eng.conv(to_fmap(x.cuda()), ups[i][j], out=up, scatter=(2, i, 2, j))
     assert relerr(up.nchw(), F.conv_transpose2d(x.double(), wt.double(), stride=2)) < 2e-5
+
+
+@pytest.mark.parametrize('impl,tol', [(1, 2e-6), (3, 3e-6)])
+def test_rowpacked_stem_conv_matches_fp64(impl, tol):
+    """7x7 s2 p3 conv on 3 channels as a 7x1 conv over 32 row-packed "channels" of a zero-bordered channels-last image
+    (tt_conv_desc.x_hstride, x_ld < Cin): SIMT and tcgen05 against torch fp64."""
+    from thinktwice_b200 import lib
+    from thinktwice_b200.engine import Engine, FMap
+    from thinktwice_b200.weights import Packer
+    gen = torch.Generator().manual_seed(21)
+    N, H, W, Cout = 2, 36, 52, 64
+    x = torch.randn(N, 3, H, W, generator=gen)
+    w = torch.randn(Cout, 3, 7, 7, generator=gen) * 0.08
+    eng = Engine('cuda:0', impl=impl)
+    eng.tc_min_rows = 1
+    pw = Packer({'c.weight': w}, torch.device('cuda:0'), tc_mode=impl).conv_rowpacked('c')
+    pb = eng.nchw_to_nhwc_padded(x.cuda(), 't.img', 4, 3, 3, 3, 5)
+    assert float(pb[:, :3].abs().max()) == 0 and float(pb[:, :, :3].abs().max()) == 0 and float(pb[:, :, W + 3:].abs().max()) == 0
+    Wp = W + 8
+    n0 = lib.launch_count()
+    y = eng.conv(FMap(pb, N, H + 6, W, 32, ld=4), pw, name='t.stem', stride=2, act=1, x_hstride=Wp * 4, x_nstride=(H + 6) * Wp * 4)
+    torch.cuda.synchronize()
+    assert lib.launch_count() - n0 == 1
+    ref = F.relu(F.conv2d(x.double(), w.double(), stride=2, padding=3))
+    assert y.H == ref.shape[2] and y.W == ref.shape[3]
+    assert relerr(y.nchw(), ref) < tol

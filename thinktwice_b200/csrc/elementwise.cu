@@ -16,7 +16,7 @@ inline int blocks_for(long long n, int cap = 148 * 16) {
 
 // ---- NCHW <-> NHWC through a 32x32 shared-memory transpose tile (both sides coalesced)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int y_ld,
-                                    int y_coff, int cpad) {
+                                    int y_coff, int cpad, int W, int out_W, long long out_HW, int top, int left) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -27,7 +27,10 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
-    if (p < HW && c < cpad) y[((long long)n * HW + p) * y_ld + y_coff + c] = tile[threadIdx.x][i];
+    if (p < HW && c < cpad) {
+      const int h = p / W, w = p - h * W;                        // destination may be a larger (zero-bordered) image
+      y[((long long)n * out_HW + (long long)(h + top) * out_W + w + left) * y_ld + y_coff + c] = tile[threadIdx.x][i];
+    }
   }
 }
 
@@ -241,8 +244,19 @@ int tt_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, int y_
                     tt_stream_t stream) {
   TT_REQUIRE(x && y && cpad >= C, "tt_nchw_to_nhwc", "bad arguments");
   dim3 grid(tt_cdiv((long long)H * W, 32), tt_cdiv(cpad, 32), N), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, C, H * W, y_ld, y_coff, cpad);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, C, H * W, y_ld, y_coff, cpad, W, W, (long long)H * W, 0, 0);
   TT_LAUNCHED("tt_nchw_to_nhwc");
+  return TT_OK;
+}
+
+int tt_nchw_to_nhwc_padded(const float* x, float* y, int N, int C, int H, int W, int y_ld, int cpad, int out_H, int out_W,
+                           int top, int left, tt_stream_t stream) {
+  TT_REQUIRE(x && y && cpad >= C && top >= 0 && left >= 0 && top + H <= out_H && left + W <= out_W, "tt_nchw_to_nhwc_padded",
+             "bad arguments");
+  dim3 grid(tt_cdiv((long long)H * W, 32), tt_cdiv(cpad, 32), N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, C, H * W, y_ld, 0, cpad, W, out_W, (long long)out_H * out_W,
+                                                                top, left);
+  TT_LAUNCHED("tt_nchw_to_nhwc_padded");
   return TT_OK;
 }
 

@@ -75,7 +75,8 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const TileSel& ts, 
     iw0 = ow * d.stride - d.pad;
   }
   const float* xg = p.x + d.x_coff + g * p.Cin_g;
-  const long long xns = d.x_nstride ? d.x_nstride : (long long)d.H * d.W * d.x_ld;
+  const long long xhs = d.x_hstride ? d.x_hstride : (long long)d.W * d.x_ld;
+  const long long xns = d.x_nstride ? d.x_nstride : (long long)d.H * xhs;
   const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
 
   // ---- B loader state
@@ -106,7 +107,7 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const TileSel& ts, 
             const int kh = tap / d.KW, kw = tap - kh * d.KW;
             const int ih = ih0 + kh * d.dil, iw = iw0 + kw * d.dil;
             if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W)
-              src = xg + an * xns + ((long long)ih * d.W + iw) * d.x_ld + c;
+              src = xg + an * xns + ih * xhs + (long long)iw * d.x_ld + c;
           }
           if (src) v = __ldg(reinterpret_cast<const float4*>(src));
         }
@@ -126,7 +127,7 @@ __device__ __forceinline__ void conv_tile(const ConvArgs& p, const TileSel& ts, 
                 const int kh = tap / d.KW, kw = tap - kh * d.KW;
                 const int ih = ih0 + kh * d.dil, iw = iw0 + kw * d.dil;
                 if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W)
-                  e[i] = __ldg(xg + an * xns + ((long long)ih * d.W + iw) * d.x_ld + c);
+                  e[i] = __ldg(xg + an * xns + ih * xhs + (long long)iw * d.x_ld + c);
               }
             }
           }
@@ -422,7 +423,7 @@ int tt_conv2d_simt(const tt_conv_desc* d, const float* x, const float* w, const 
   a.partial = static_cast<float*>(workspace);
   a.out_index = nullptr;
   a.accumulate = 0;
-  const bool veca = (a.Cin_g % 4 == 0) && (d->x_ld % 4 == 0) && (d->x_coff % 4 == 0) && (d->x_nstride % 4 == 0) &&
+  const bool veca = (a.Cin_g % 4 == 0) && (d->x_ld % 4 == 0) && (d->x_coff % 4 == 0) && (d->x_nstride % 4 == 0) && (d->x_hstride % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const bool vecb = (a.Cout_g % 4 == 0) && (d->Cout % 4 == 0) && (d->y_nstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
                     (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&

@@ -602,7 +602,7 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
 
 bool tt_conv2d_tc_supported(const tt_conv_desc* d, const void* x, const void* w, const void* y) {
   if (d->groups != 1 || (d->stride != 1 && d->stride != 2)) return false;
-  if (d->Cin % 4 || d->Cout % 4 || d->x_ld % 4 || d->x_coff % 4 || d->y_ld % 4 || d->x_nstride % 4 || d->y_nstride % 4) return false;
+  if (d->Cin % 4 || d->Cout % 4 || d->x_ld % 4 || d->x_coff % 4 || d->y_ld % 4 || d->x_nstride % 4 || d->y_nstride % 4 || d->x_hstride % 4) return false;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return false;
   if (d->res_mode != TT_RES_NONE && (d->res_ld % 4)) return false;
   if (d->res2_ld % 4) return false;
@@ -628,7 +628,8 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   const int terms = d->impl == 3 ? 3 : 1;
   const int taps = d->KH * d->KW;
   const long long npix_in = (long long)d->N * d->H * d->W;
-  const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * d->W * d->x_ld;
+  const long long xhs = d->x_hstride ? d->x_hstride : (long long)d->W * d->x_ld;   // input row pitch
+  const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * xhs;
   const float* xa = x + d->x_coff;                            // TMA reads the activation tensor in place (ld / coff / image stride)
   TcArgs a;
   a.d = *d;
@@ -637,7 +638,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk (set to 2 for BN = 256)
   a.n_slabs = (d->Cin + KS - 1) / KS;
   a.total_pix = d->N * d->OH * d->OW;
-  a.flat = (taps == 1 && d->pad == 0 && d->stride == 1 && xns == (long long)d->H * d->W * d->x_ld) ? 1 : 0;
+  a.flat = (taps == 1 && d->pad == 0 && d->stride == 1 && xhs == (long long)d->W * d->x_ld && xns == (long long)d->H * xhs) ? 1 : 0;
   CUtensorMap ma, mb_hi, mb_lo;
   int grid_x;
   if (a.flat) {
@@ -661,7 +662,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     a.TH = best_th; a.TW = best_tw;
     a.tiles_w = tt_cdiv(d->OW, a.TW); a.tiles_h = tt_cdiv(d->OH, a.TH);
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t str[3] = {(cuuint64_t)d->x_ld * 4, (cuuint64_t)d->W * d->x_ld * 4, (cuuint64_t)xns * 4};
+    cuuint64_t str[3] = {(cuuint64_t)d->x_ld * 4, (cuuint64_t)xhs * 4, (cuuint64_t)xns * 4};
     cuuint32_t box[4] = {KS, (cuuint32_t)(a.TW * d->stride), (cuuint32_t)(a.TH * d->stride), 1};
     if (!encode_map(&ma, xa, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
     grid_x = a.tiles_w * a.tiles_h * d->N;

@@ -43,11 +43,12 @@ class FMap:
 
 class PackedConv:
     """weights of one conv / linear in kernel layout: w [taps*Cin_g][Cout] (BatchNorm folded), bias [Cout]|None."""
-    __slots__ = ('w', 'bias', 'Cin', 'Cout', 'KH', 'KW', 'groups', 'w_tc')
+    __slots__ = ('w', 'bias', 'Cin', 'Cout', 'KH', 'KW', 'groups', 'w_tc', 'alg_k')
 
     def __init__(self, w, bias, Cin, Cout, KH=1, KW=1, groups=1, w_tc=None):
         self.w, self.bias, self.Cin, self.Cout, self.KH, self.KW, self.groups = w, bias, Cin, Cout, KH, KW, groups
         self.w_tc = w_tc            # [2][Cout][taps][Cin] TF32 hi / lo planes for the tcgen05 path (or None)
+        self.alg_k = None           # algorithmic K per output (row-packed convs carry zero-weight padding)
 
 
 class _SideBranch:
@@ -148,7 +149,7 @@ class Engine:
 
     # ------------------------------------------------------------------ conv / linear
     def conv(self, x, pw, out=None, name=None, stride=1, pad=0, dil=1, act=0, res=None, res_mode=0, res2=None,
-             scatter=None, out_ld=None, impl=None, x_nstride=0, y_nstride=0, n_images=None, bias_n_mod=0):
+             scatter=None, out_ld=None, impl=None, x_nstride=0, y_nstride=0, n_images=None, bias_n_mod=0, x_hstride=0):
         """y = act(conv(x) + bias + res + res2).  `out` (FMap) selects the destination (concat slice / scatter
         target); otherwise a buffer `name` is created.  scatter = (oy_mul, oy_add, ox_mul, ox_add)."""
         assert x.C == pw.Cin, (x.C, pw.Cin, name)
@@ -158,7 +159,7 @@ class Engine:
             out = self.fmap(name, x.N, OH, OW, pw.Cout, out_ld)
         d = ConvDesc()
         d.N, d.H, d.W, d.Cin, d.x_ld, d.x_coff = (n_images or x.N), x.H, x.W, x.C, x.ld, 0
-        d.x_nstride, d.y_nstride = x_nstride, y_nstride
+        d.x_nstride, d.y_nstride, d.x_hstride = x_nstride, y_nstride, x_hstride
         d.Cout, d.KH, d.KW, d.stride, d.pad, d.dil, d.groups = pw.Cout, pw.KH, pw.KW, stride, pad, dil, pw.groups
         d.OH, d.OW = OH, OW
         d.y_ld, d.y_coff, d.yH, d.yW = out.ld, 0, out.H, out.W
@@ -182,7 +183,7 @@ class Engine:
         use_tc = (impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and stride in self.tc_strides and pw.groups == 1
                   and x.ld % 4 == 0 and x.coff % 4 == 0 and out.ld % 4 == 0 and out.coff % 4 == 0
                   and (res is None or (res.ld % 4 == 0 and res.coff % 4 == 0)) and (res2 is None or (res2.ld % 4 == 0 and res2.coff % 4 == 0))
-                  and x_nstride % 4 == 0 and y_nstride % 4 == 0
+                  and x_nstride % 4 == 0 and y_nstride % 4 == 0 and x_hstride % 4 == 0
                   and d.N * OH * OW >= self.tc_min_rows and pw.Cout >= 32)
         d.impl = impl if use_tc else lib.IMPL_SIMT
         ws = None
@@ -200,7 +201,7 @@ class Engine:
             None, None, _p(out.t, out.coff), _p(ws), _stream()), f'tt_conv2d[{name}]')
         if self.prof is not None:
             ev1.record()
-            flops = 2.0 * d.N * OH * OW * (pw.KH * pw.KW * pw.Cin // pw.groups) * pw.Cout
+            flops = 2.0 * d.N * OH * OW * (pw.alg_k or pw.KH * pw.KW * pw.Cin // pw.groups) * pw.Cout
             self.prof.append((name, flops, ev0, ev1))
         return out
 
@@ -239,6 +240,14 @@ class Engine:
         cpad = cpad or Cc
         out = self.fmap(name, N, H, W, cpad)
         lib.call('tt_nchw_to_nhwc', _p(x), _p(out.t), N, Cc, H, W, out.ld, 0, cpad)
+        return out
+
+    def nchw_to_nhwc_padded(self, x, name, cpad, top, bottom, left, right):
+        """NCHW -> channels-last inside a zero-bordered [N][top+H+bottom][left+W+right][cpad] buffer (zeroed once at
+        allocation; the border is never written afterwards).  Returns the raw buffer."""
+        N, Cc, H, W = x.shape
+        out = self.buf(name, (N, top + H + bottom, left + W + right, cpad), zero=True)
+        lib.call('tt_nchw_to_nhwc_padded', _p(x), _p(out), N, Cc, H, W, cpad, cpad, top + H + bottom, left + W + right, top, left)
         return out
 
     def nhwc_to_nchw(self, x, name):

@@ -23,7 +23,7 @@ class TTError(RuntimeError):
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ('N', 'H', 'W', 'Cin', 'x_ld', 'x_coff')] + \
-               [('x_nstride', C.c_longlong), ('y_nstride', C.c_longlong)] + \
+               [('x_nstride', C.c_longlong), ('y_nstride', C.c_longlong), ('x_hstride', C.c_longlong)] + \
                [(n, C.c_int) for n in ('Cout', 'KH', 'KW', 'stride', 'pad', 'dil', 'groups', 'OH', 'OW',
                                         'y_ld', 'y_coff', 'yH', 'yW', 'oy_mul', 'oy_add', 'ox_mul', 'ox_add',
                                         'act', 'bias_n_mod', 'res_mode', 'res_ld', 'res_coff', 'res_H', 'res_W',
@@ -87,7 +87,7 @@ def load():
 
 EXPORTS = [
     'tt_version', 'tt_last_error', 'tt_launch_count', 'tt_voxel_pooling_workspace_bytes', 'tt_voxel_pooling_forward',
-    'tt_lift_splat_workspace_bytes', 'tt_lift_splat', 'tt_conv2d', 'tt_conv2d_workspace_bytes', 'tt_nchw_to_nhwc', 'tt_nhwc_to_nchw',
+    'tt_lift_splat_workspace_bytes', 'tt_lift_splat', 'tt_conv2d', 'tt_conv2d_workspace_bytes', 'tt_nchw_to_nhwc', 'tt_nchw_to_nhwc_padded', 'tt_nhwc_to_nchw',
     'tt_maxpool3x3s2', 'tt_upsample2x_bilinear_ac', 'tt_global_avgpool', 'tt_broadcast_rows', 'tt_se_gate', 'tt_se_pool',
     'tt_se_apply', 'tt_anti_transpose', 'tt_copy2d', 'tt_layernorm', 'tt_eltwise', 'tt_fill', 'tt_dcn_im2col',
     'tt_voxelize_workspace_bytes', 'tt_voxelize_mean', 'tt_rulebook_workspace_bytes', 'tt_sparse_rulebook',

@@ -51,7 +51,7 @@ class LSS:
         p = self.prefix
         w = self.w = {}
         b = p + 'img_backbone.'
-        w['stem'] = pk.conv(b + 'conv1', bn=b + 'bn1', cin_pad=4)
+        w['stem'] = pk.conv_rowpacked(b + 'conv1', bn=b + 'bn1', cpad=4, kslab=32)   # 7x7x3 s2: 7 row-packed K slabs
         self.blocks = []
         for li, n in enumerate([3, 4, 6, 3]):
             for i in range(n):
@@ -88,9 +88,11 @@ class LSS:
             w[f'u{l}_up'] = pk.convT(f'{u}unet_layer{l}.up')
             w[f'u{l}_conv'] = pk.conv(f'{u}unet_layer{l}.conv_relu.0')
         w['u0_a'] = pk.conv(u + 'unet_layer0.1'); w['u0_b'] = pk.conv(u + 'unet_layer0.3')
-        w['seg_last'] = pk.conv(u + 'conv_last')
+        w['seg_last'] = pk.conv(u + 'conv_last', cout_pad=32)          # 12 -> 32 zero-padded channels: tcgen05 instead of SIMT
+        self.seg_classes = int(pk.sd[u + 'conv_last.weight'].shape[0])
         r = p + 'seg_res_to_image_feature.'
-        w['s2f'] = [pk.conv(f'{r}{3 * i}', bn=f'{r}{3 * i + 1}') for i in range(7)]
+        w['s2f'] = [pk.conv(f'{r}{3 * i}', bn=f'{r}{3 * i + 1}', cout_pad=32) for i in range(7)]   # s2f.1 is 64 -> 16
+        self.s2f_channels = [int(pk.sd[f'{r}{3 * i}.weight'].shape[0]) for i in range(7)]
         w['merge'] = pk.conv(p + 'merge_seg_and_image')
         if self.queue_len != 1:
             w['sweep_merge'] = pk.conv(p + 'bev_multiframe_merge')
@@ -131,7 +133,6 @@ class LSS:
     # ------------------------------------------------------------------ sub-graphs
     def _backbone(self, x):
         e, w = self.eng, self.w
-        x = e.conv(x, w['stem'], name='rs.stem', stride=2, pad=3, act=ACT_RELU)
         x = e.maxpool3x3s2(x, 'rs.pool')
         outs = []
         for bi, blk in enumerate(self.blocks):
@@ -213,7 +214,7 @@ class LSS:
         d = e.upsample2x(d, 'un.up0')
         d = e.conv(d, w['u0_a'], name='un.d0a', pad=1, act=ACT_RELU)
         d = e.conv(d, w['u0_b'], name='un.d0b', pad=1)
-        return e.conv(d, w['seg_last'], name='seg')
+        return e.conv(d, w['seg_last'], name='seg').slice(0, self.seg_classes)
 
     def _seg_to_feat(self, seg, out):
         e, w = self.eng, self.w
@@ -222,13 +223,22 @@ class LSS:
         for i, (k, s) in enumerate(spec):
             last = i == len(spec) - 1
             x = e.conv(x, w['s2f'][i], out=out if last else None, name=f's2f.{i}', stride=s, pad=k // 2, act=ACT_RELU)
+            x = x.slice(0, self.s2f_channels[i]) if not last else x
         return x
 
     def _single_sweep(self, imgs, s, bev_out):
         """lss.py:542-621 for one sweep; imgs (B, N, 3, H, W) NCHW on the device; s = sweep distance from the key frame."""
         e, w = self.eng, self.w
         B, N = imgs.shape[:2]
-        x = e.nchw_to_nhwc(imgs.reshape(B * N, *imgs.shape[2:]), 'img.nhwc', cpad=4)
+        # stem (ResNet conv1 7x7 s2 p3 on 3 channels): the image goes channels-last (4 floats / pixel) into a buffer with
+        # a physical zero border (3 px top / bottom / left, 5 right), so a tap ROW of 7 px x 4 floats is 28 contiguous
+        # floats = one 32-float K slab of a 7x1 conv over 32 "channels" (x_ld = 4 < Cin = 32, row pitch x_hstride)
+        im = imgs.reshape(B * N, *imgs.shape[2:])
+        H0, W0 = im.shape[2:]
+        pb = e.nchw_to_nhwc_padded(im, 'img.nhwc', 4, 3, 3, 3, 5)
+        Wp = W0 + 8
+        x = e.conv(FMap(pb, B * N, H0 + 6, W0, 32, ld=4), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
+                   x_hstride=Wp * 4, x_nstride=(H0 + 6) * Wp * 4)
         fpn = self._pafpn(self._backbone(x))
         src = e.conv(fpn[2], w['neck_conv'], name='img_feats')
         mlp_in = e.wrap(e.static('in.mlp_in').view(B * N, 1, 1, 24))

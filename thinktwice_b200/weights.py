@@ -79,6 +79,27 @@ class Packer:
         w_tc = self._tc(w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cg)) if groups == 1 else None
         return PackedConv(self._dev(packed), self._dev(b), Cg * groups, Cout, KH, KW, groups, w_tc)
 
+    def conv_rowpacked(self, n, bn=None, eps=1e-5, cpad=4, kslab=32):
+        """thin-channel Conv2d (Cout, Cin<=cpad, KH, KW) [+BN] as a KH x 1 conv whose "channels" are the KW*cpad floats
+        of a tap row, contiguous in a channels-last image with `cpad` floats per pixel (tt_conv_desc.x_hstride).
+        K per kernel row = kslab (>= KW*cpad, zero weights in the tail): the 7x7x3 stem becomes 7 full 32-float K slabs
+        instead of 49 slabs with 3 of 32 lanes in use."""
+        w = self.sd[n + '.weight'].double()
+        b = self.sd.get(n + '.bias')
+        b = b.double() if b is not None else None
+        if bn is not None:
+            s, t = bn_affine(self.sd, bn, eps)
+            w = w * s.view(-1, 1, 1, 1)
+            b = t if b is None else b * s + t
+        Cout, Cin, KH, KW = w.shape
+        assert Cin <= cpad and KW * cpad <= kslab
+        wk = w.new_zeros(Cout, KH, kslab)                                # [co][kh][kw * cpad + c]
+        wk.view(Cout, KH, kslab // cpad, cpad)[:, :, :KW, :Cin] = w.permute(0, 2, 3, 1)
+        pc = PackedConv(self._dev(wk.permute(1, 2, 0).reshape(KH * kslab, Cout)), self._dev(b), kslab, Cout, KH, 1,
+                        w_tc=self._tc(wk))
+        pc.alg_k = KH * KW * Cin
+        return pc
+
     def conv_group_gemms(self, n, groups):
         """grouped Conv2d weight (Cout, Cin_g, KH, KW) -> one dense GEMM per group over im2col columns laid out
         [group][tap][Cin_g] (tt_dcn_im2col): list of PackedConv with Cin = KH*KW*Cin_g, Cout = Cout/groups."""
