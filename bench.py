@@ -211,7 +211,7 @@ def main():
         return float(ms.item())
 
     if args.tc_reserve or args.dbg:
-        lib.load().tt_debug_set((args.tc_reserve << 8) | args.dbg)
+        lib.load().tt_debug_set((args.tc_reserve << 8) | (args.dbg & 0xFF) | ((args.dbg >> 8) << 16))
     n_eager = lib.launch_count()
     step(resident)                                               # eager step: allocates every buffer, counts launches
     torch.cuda.synchronize()

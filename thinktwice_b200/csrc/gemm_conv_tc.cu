@@ -10,17 +10,24 @@
 //   * the raw fp32 activation slab is what TMA delivers; two "split" warps rewrite it in shared memory as hi (in place)
 //     and lo (second buffer) before the MMA thread may touch it — no pre-pass over the activations, no lo plane
 //     streamed from L2 (the kernel's roof is L2->SM ingest: profiles/r1_summary_tc.md);
-//   * precision: fp32 operands are split x = hi + lo with hi, lo both TF32-representable (round-to-nearest), and
-//     every K slab issues hi*hi + hi*lo + lo*hi ("3xTF32": ~21 mantissa bits per operand).  The tensor core adds
-//     into its fp32 accumulator with truncation, an error that grows linearly with the number of accumulations
-//     (measured: ~8e-9 * K relative), so (a) the two small correction products go to their OWN TMEM accumulator and
-//     (b) every CHUNK K-slabs the epilogue warps drain both accumulators with tcgen05.ld and fold them into fp32
-//     registers with round-to-nearest FADDs while the MMA warp already fills the other accumulator pair (TMEM
-//     ping-pong: 2 x (main + corr) x BN columns = all 512 columns at BN = 128).  impl == TF32x1 issues hi*hi only;
-//   * epilogue: 4 warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per instruction), fuse
-//     bias + residual(s) + activation and store 128-bit channels-last rows (concat offset / pixel scatter
-//     for transposed convs handled in the store address).
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//   * precision: fp32 operands are split x = hi + lo (activations: hi = RN_tf32(x), lo = x - hi, split in shared
+//     memory; weights: hi / lo planes prepared once on the host) and every K slab issues hi*hi + hi*lo + lo*hi
+//     ("3xTF32": ~21 mantissa bits per operand) as TWO instructions: A_hi x [B_hi ; B_lo] with N = 2 BN (the lo weight
+//     tile follows the hi tile in shared memory, the correction accumulator follows the main one in TMEM) and
+//     A_lo x B_hi.  The tensor core adds into its fp32 accumulator with truncation, an error that grows linearly with
+//     the number of accumulations (measured: ~8e-9 * K relative), so (a) the two small correction products have their
+//     OWN TMEM accumulator and (b) every CHUNK K-slabs the epilogue warps drain both accumulators with tcgen05.ld and
+//     fold them into fp32 registers with round-to-nearest FADDs while the MMA warp already fills the other accumulator
+//     pair (TMEM ping-pong: 2 x (main + corr) x BN columns = all 512 columns at BN = 128).  impl == TF32x1: hi*hi only;
+//   * epilogue: 8 warps (two per TMEM lane quarter) read the accumulators with tcgen05.ld, transpose through warp-
+//     private shared-memory slabs and store coalesced channels-last rows with bias + residual(s) + activation fused
+//     (concat offset / pixel scatter for transposed convs handled in the store address);
+//   * persistent CTA pairs (cluster of 2): both CTAs walk the same (M-tile pair, N tile) list, each loads half of the
+//     weight slab and TMA-multicasts it to its peer;
+//   * split-K for under-filled layers (few tiles, long K) and GATHER mode (tap-major sparse convolution: cp.async row
+//     gather) both end in a red.add.v4.f32 epilogue into a pre-initialised output.
+// Warp roles: warp 0 = TMA / gather producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue,
+// warps 10..11 = operand split.
 #include <cuda.h>
 #include <string.h>
 
@@ -150,6 +157,9 @@ struct TcArgs {
   const int* pairs_out;  // [kvol][pair_cap]
   const int* pair_count; // [kvol]
   int kvol, pair_cap;
+  // split-K (under-filled layers: few tiles, long K): work item = (tile pair, N tile, K split); partial sums are
+  // red.add-ed into an output the host pre-initialised with bias + residuals, activation applied by a finish kernel
+  int splits, k_per;     // K slabs per split (k_per * splits >= taps * n_slabs)
 };
 constexpr int MAX_KVOL = 32;
 
@@ -187,7 +197,7 @@ TT_DEVICE void split_rn(float x, float& hi, float& lo) {
 // are (tap, pair-tile pair, N tile); warp 0 gathers the activation rows of a tile with 16-byte cp.async (zero-fill for
 // the tile tail / channel tail) straight into the 128-byte-swizzled stage buffer, signalling the same `full` barrier
 // the weight TMA uses; the epilogue accumulates into the bias-initialised output rows with red.add.v4.f32.
-template <int BN, int STAGES, bool MERGED, bool GATHER>
+template <int BN, int STAGES, bool GATHER>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
@@ -195,9 +205,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int A_BYTES = BM * KS * 4;                    // 16 KB
   constexpr int B_BYTES = BN * KS * 4;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  // TMEM: 2 (ping-pong) x {main, corr} x BN fp32 columns; MERGED (BN = 256): the correction products share the main
-  // accumulator (2 x BN columns) and chunks are shorter instead, so the truncating accumulations per chunk stay ~24.
-  constexpr int ACC_COLS = MERGED ? BN : 2 * BN;
+  // TMEM: 2 (ping-pong) x {main, corr} x BN fp32 columns (all 512 columns at BN = 128)
+  constexpr int ACC_COLS = 2 * BN;
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   constexpr int SLAB = 16;                                // epilogue slab: 16 columns of a warp's 32 rows
   constexpr int PITCH = SLAB + 4;                         // +4 floats: conflict-free transposition
@@ -222,7 +231,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = d.KH * d.KW;
   const int k_iters = taps * p.n_slabs;
-  const int n_chunks = (k_iters + p.chunk - 1) / p.chunk;
   const uint32_t rank = cluster_ctarank();                // 0 / 1 inside the CTA pair
   const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 
@@ -253,9 +261,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // both CTAs iterate the same pair list (lockstep)
-  const int total_pairs = GATHER ? sp_first[p.kvol] * p.n_tiles : ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int total_pairs = (GATHER ? sp_first[p.kvol] : (p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
   // work item -> (N tile, M tile of this CTA, tap, rows of that tap)
-  auto decode = [&](int pt, int& nt, int& mt, int& tap, int& count) {
+  auto decode = [&](int pt, int& nt, int& mt, int& tap, int& count, int& kb, int& ke) {
+    const int ks = pt % p.splits;
+    pt /= p.splits;
+    kb = ks * p.k_per;
+    ke = min(k_iters, kb + p.k_per);
     nt = pt % p.n_tiles;
     const int pm = pt / p.n_tiles;
     tap = 0; count = 0;
@@ -273,8 +285,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t txb = (p.terms == 3 ? 2 : 1) * B_BYTES;
     int ig = 0;
     for (int pt = pair0; pt < total_pairs; pt += pair_step) {
-      int nt, mt, tap, count;
-      decode(pt, nt, mt, tap, count);
+      int nt, mt, tap, count, kb, ke;
+      decode(pt, nt, mt, tap, count, kb, ke);
       const int n0 = nt * BN;
       const int* pin = p.pairs_in + (long long)tap * p.pair_cap;
       int rows[4];                                            // this lane's rows: lane, lane + 32, lane + 64, lane + 96
@@ -283,7 +295,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m = mt * BM + lane + 32 * i;
         rows[i] = m < count ? __ldg(pin + m) : -1;
       }
-      for (int it = 0; it < k_iters; ++it, ++ig) {
+      for (int it = kb; it < ke; ++it, ++ig) {
         const int s = ig % STAGES;
         mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
         uint8_t* st = smem + s * STAGE_BYTES;
@@ -315,7 +327,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t tx = ((p.dbg & 2) ? 0u : a_box) + (p.terms == 3 ? 2 : 1) * B_BYTES;     // own raw A + both weight halves
       int ig = 0;                                                               // ring position, continues across tiles
       for (int pt = pair0; pt < total_pairs; pt += pair_step) {
-        const int nt = pt % p.n_tiles, mt = 2 * (pt / p.n_tiles) + (int)rank;     // mt >= m_tiles: dummy tile, TMA zero-fills
+        int nt, mt, tap0, count, kb, ke;                                        // mt >= m_tiles: dummy tile, TMA zero-fills
+        decode(pt, nt, mt, tap0, count, kb, ke);
         const int n0 = nt * BN;
         int cw0, ch0, cn;
         if (p.flat) { cw0 = mt * BM; ch0 = 0; cn = 0; }
@@ -324,7 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           cn = mt / (p.tiles_w * p.tiles_h);
           cw0 = tw * p.TW * d.stride - d.pad; ch0 = th * p.TH * d.stride - d.pad;
         }
-        for (int it = 0; it < k_iters; ++it, ++ig) {
+        for (int it = kb; it < ke; ++it, ++ig) {
           const int s = ig % STAGES;
           mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
@@ -344,16 +357,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      constexpr uint32_t idesc2 = make_idesc(BM, MERGED ? BN : 2 * BN);   // hi*hi | hi*lo in one instruction
+      constexpr uint32_t idesc2 = make_idesc(BM, 2 * BN);                 // hi*hi | hi*lo in one instruction
       int ig = 0, cg = 0;                                                       // ring / chunk counters across tiles
       for (int pt = pair0; pt < total_pairs; pt += pair_step) {
-        int it = 0;
-        for (int c = 0; c < n_chunks; ++c, ++cg) {
+        int nt, mt, tap0, count, kb, ke;
+        decode(pt, nt, mt, tap0, count, kb, ke);
+        int it = kb;
+        const int nch = (ke - kb + p.chunk - 1) / p.chunk;
+        for (int c = 0; c < nch; ++c, ++cg) {
           const int b = cg & 1;
           mbar_wait(&acc_empty[b], ((cg >> 1) & 1) ^ 1);     // epilogue has drained this accumulator pair
           tcgen05_fence_after();
-          const uint32_t t_main = tmem_base + (uint32_t)(b * ACC_COLS), t_corr = MERGED ? t_main : t_main + BN;
-          const int it_end = min(it + p.chunk, k_iters);
+          const uint32_t t_main = tmem_base + (uint32_t)(b * ACC_COLS), t_corr = t_main + BN;
+          const int it_end = min(it + p.chunk, ke);
           bool first = true;
           for (; it < it_end; ++it, ++ig) {
             const int s = ig % STAGES;
@@ -366,7 +382,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (p.dbg & 4) break;
               const uint32_t off = kk * 32;
               const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-              if (p.terms == 3 && !MERGED && !(p.dbg & 32)) {
+              if (p.terms == 3 && !(p.dbg & 32)) {
                 // A_hi x [B_hi ; B_lo] as ONE N = 2 BN instruction: the lo weight tile follows the hi tile in shared
                 // memory and the correction accumulator follows the main one in TMEM, so hi*hi and hi*lo share a
                 // single read of the A_hi slab (the tf32 SS-MMA rate is shared-memory-read bound).
@@ -375,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               } else {
                 umma_tf32(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);
                 if (p.terms == 3) {
-                  umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, 1u);
+                  umma_tf32(t_corr, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, acc);
                   umma_tf32(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);
                 }
               }
@@ -394,7 +410,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int w2 = warp - 10;
     int ig = 0;
     for (int pt = pair0; pt < total_pairs; pt += pair_step) {
-      for (int it = 0; it < k_iters; ++it, ++ig) {
+      int nt, mt, tap0, count, kb, ke;
+      decode(pt, nt, mt, tap0, count, kb, ke);
+      for (int it = kb; it < ke; ++it, ++ig) {
         const int s = ig % STAGES;
         mbar_wait(&full[s], (ig / STAGES) & 1);
         const uint32_t raw = smem_u32(smem + s * STAGE_BYTES) + w2 * (A_BYTES / 2) + lane * 16;   // lo at + A_BYTES
@@ -429,8 +447,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* tile = tile_all + (warp - 2) * 32 * PITCH;      // warp-private transposition buffer [32 rows][PITCH]
     int cg = 0;
     for (int pt = pair0; pt < total_pairs; pt += pair_step) {
-      int nt, mt, tap, count;
-      decode(pt, nt, mt, tap, count);
+      int nt, mt, tap, count, kb, ke;
+      decode(pt, nt, mt, tap, count, kb, ke);
+      const int nch = (ke - kb + p.chunk - 1) / p.chunk;
       const bool real_tile = GATHER ? mt * BM < count : mt < p.m_tiles;
       const int n0 = nt * BN + half * HN;
       // ---- this thread's row -> output / residual addresses (once per tile); prefetch the residual lines into L2
@@ -487,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float sum[HN];
 #pragma unroll
       for (int j = 0; j < HN; ++j) sum[j] = 0.f;
-      for (int c = 0; c < n_chunks; ++c, ++cg) {
+      for (int c = 0; c < nch; ++c, ++cg) {
         const int b = cg & 1;
         mbar_wait(&acc_full[b], (cg >> 1) & 1);
         tcgen05_fence_after();
@@ -496,7 +515,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c0 = 0; c0 < HN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_main + c0, v);
-          if (p.terms == 3 && !MERGED) {
+          if (p.terms == 3) {
             uint32_t u[32];
             tmem_ld32(t_main + BN + c0, u);
 #pragma unroll
@@ -547,7 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const float4 o = make_float4(acc4[i].x + bv.x + ra[i].x + rb[i].x, acc4[i].y + bv.y + ra[i].y + rb[i].y,
                                          acc4[i].z + bv.z + ra[i].z + rb[i].z, acc4[i].w + bv.w + ra[i].w + rb[i].w);
             float* dst = p.y + ((p.dbg & 8) ? (long long)(threadIdx.x * 4) : yo[i] + col);   // dbg 8: all stores hit one hot 2 KB
-            if (GATHER) {                                      // taps race on an output row: accumulate with red.add
+            if (GATHER || p.splits > 1) {                      // taps / K splits race on an output row: red.add
               tt_red_add_v4(dst, o.x, o.y, o.z, o.w);
             } else if (!(p.dbg & 16) || o.x == 12345.678f) {                                 // dbg 16: no store at all
               *reinterpret_cast<float4*>(dst) =
@@ -565,6 +584,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// split-K companions: y = bias + res + res2 before the tensor-core kernel red.adds its partial sums; y = act(y) after
+__global__ void splitk_init_kernel(const tt_conv_desc d, const float* __restrict__ bias, const float* __restrict__ res,
+                                   const float* __restrict__ res2, float* __restrict__ y) {
+  const int HWo = d.OH * d.OW, C4 = d.Cout / 4;
+  const long long total = (long long)d.N * HWo * C4;
+  const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long pix = i / C4;
+    const int n = (int)(pix / HWo);
+    float4 v = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) { const float4 t = *reinterpret_cast<const float4*>(res + pix * d.res_ld + d.res_coff + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    if (res2) { const float4 t = *reinterpret_cast<const float4*>(res2 + pix * d.res2_ld + d.res2_coff + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    *reinterpret_cast<float4*>(y + n * yns + (pix - (long long)n * HWo) * d.y_ld + d.y_coff + c) = v;
+  }
+}
+__global__ void splitk_finish_kernel(const tt_conv_desc d, float* __restrict__ y) {
+  const int HWo = d.OH * d.OW, C4 = d.Cout / 4;
+  const long long total = (long long)d.N * HWo * C4;
+  const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long pix = i / C4;
+    const int n = (int)(pix / HWo);
+    float4* q = reinterpret_cast<float4*>(y + n * yns + (pix - (long long)n * HWo) * d.y_ld + d.y_coff + c);
+    const float4 v = *q;
+    *q = make_float4(tt_act(v.x, d.act), tt_act(v.y, d.act), tt_act(v.z, d.act), tt_act(v.w, d.act));
   }
 }
 
@@ -635,7 +684,7 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.d = *d;
   a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
   a.terms = terms;
-  a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk (set to 2 for BN = 256)
+  a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk
   a.n_slabs = (d->Cin + KS - 1) / KS;
   a.total_pix = d->N * d->OH * d->OW;
   a.flat = (taps == 1 && d->pad == 0 && d->stride == 1 && xhs == (long long)d->W * d->x_ld && xns == (long long)d->H * xhs) ? 1 : 0;
@@ -667,10 +716,8 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
     if (!encode_map(&ma, xa, 4, dims, str, box, d->stride)) return TT_ERR_CUDA;
     grid_x = a.tiles_w * a.tiles_h * d->N;
   }
-  // BN = 256 (fewer activation bytes per MMA, but a 2-stage ring and a heavier epilogue) pays off only for long-K
-  // layers with enough tiles to fill the machine (measured: 3x3 512->512 @28x56 218 -> 185 us; 1x1 layers lose).
-  const bool wide = terms == 3 && d->Cout >= 256 && taps >= 9 && d->Cin >= 256 && (long long)grid_x * tt_cdiv(d->Cout, 256) >= 74;
-  const int BN = wide ? 256 : (d->Cout > 64 ? 128 : 64);
+  // (a BN = 256 variant with merged accumulators was measured slower than BN = 128 with the fused hi*hi|hi*lo MMA: dropped)
+  const int BN = d->Cout > 64 ? 128 : 64;
   {
     const size_t wplane = (size_t)d->Cout * taps * d->Cin;
     cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)taps, (cuuint64_t)d->Cout};
@@ -684,7 +731,36 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.n_tiles = tt_cdiv(d->Cout, BN);
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-  const long long pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles;
+  // split-K: a layer with few tiles and a long K (14x28 / 21x21 / 84x84 maps) leaves most SMs idle; spread K over
+  // the idle CTA pairs.  Needs a plain output layout (no pixel scatter, SAME residuals, one bias vector).
+  const int k_iters = taps * a.n_slabs;
+  a.splits = 1;
+  a.k_per = k_iters;
+  {
+    const long long tile_pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles;
+    const bool plain = d->oy_mul == 1 && d->ox_mul == 1 && d->oy_add == 0 && d->ox_add == 0 && d->yH == d->OH && d->yW == d->OW &&
+                       d->res_mode != TT_RES_UP2_NEAREST && d->bias_n_mod == 0 && !(g_tt_debug & 128);
+    if (plain && tile_pairs * 2 <= num_sms / 2 && k_iters >= 16) {
+      int sp = (int)((num_sms / 2 + tile_pairs - 1) / tile_pairs);
+      if (sp > k_iters / 8) sp = k_iters / 8;
+      if (sp > 32) sp = 32;
+      if (sp >= 2) {
+        a.k_per = tt_cdiv(k_iters, sp);
+        a.splits = tt_cdiv(k_iters, a.k_per);
+      }
+    }
+  }
+  if (a.splits > 1) {
+    const long long total4 = (long long)d->N * d->OH * d->OW * (d->Cout / 4);
+    const int nb = (int)((total4 + 255) / 256 > 1184 ? 1184 : (total4 + 255) / 256);
+    splitk_init_kernel<<<nb, 256, 0, st>>>(*d, bias, d->res_mode != TT_RES_NONE ? res : nullptr, res2, y);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_conv2d(tc split-k init)");
+    a.bias = nullptr; a.res = nullptr; a.res2 = nullptr;
+    a.d.act = TT_ACT_NONE;
+    a.d.res_mode = TT_RES_NONE;
+  }
+  const long long pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles * a.splits;
   const long long max_pairs = (num_sms - ((g_tt_debug >> 8) & 0xFF)) / 2;        // debug bits 8..15: SMs left to a concurrent branch
   dim3 grid((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));  // persistent CTA pairs (cluster of 2), one CTA per SM
   cudaLaunchConfig_t cfg = {};
@@ -698,29 +774,35 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   cfg.numAttrs = 1;
   constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;  // 8 warp-private slabs + row tables + barriers (13 x 8 B) + tap prefix
   cudaError_t lerr;
-  if (BN == 256) {
-    a.chunk = 2;
-    constexpr int smem = 2 * (2 * BM * KS * 4 + 2 * 256 * KS * 4) + 1024 + EPI_BYTES;
-    static bool set256 = false;
-    if (!set256) { cudaFuncSetAttribute(conv_tc_kernel<256, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set256 = true; }
-    cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, 2, true, false>, ma, mb_hi, mb_lo, a);
-  } else if (BN == 128) {
+  if (BN == 128) {
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;
-    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
+    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false, false>, ma, mb_hi, mb_lo, a);
-  } else {
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false>, ma, mb_hi, mb_lo, a);
+  } else if (g_tt_debug & 0x10000) {                          // experiment: 3-stage ring for BN = 64
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
     static bool set64 = false;
-    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
+    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false, false>, ma, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false>, ma, mb_hi, mb_lo, a);
+  } else {                                                    // BN = 64 stages are 48 KB: a 4-deep ring fits
+    constexpr int smem = 4 * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
+    static bool set64 = false;
+    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
+    cfg.dynamicSmemBytes = smem;
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 4, false>, ma, mb_hi, mb_lo, a);
   }
   if (lerr != cudaSuccess) { tt_set_error("tt_conv2d(tc): cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_conv2d(tc)");
+  if (a.splits > 1 && d->act != TT_ACT_NONE) {
+    const long long total4 = (long long)d->N * d->OH * d->OW * (d->Cout / 4);
+    const int nb = (int)((total4 + 255) / 256 > 1184 ? 1184 : (total4 + 255) / 256);
+    splitk_finish_kernel<<<nb, 256, 0, st>>>(*d, y);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_conv2d(tc split-k finish)");
+  }
   return TT_OK;
 }
 
@@ -750,6 +832,7 @@ int tt_sparse_conv_tc(const tt_sparse_conv_desc* d, const float* feats_in, const
   a.gx = feats_in; a.gx_ld = d->in_ld;
   a.pairs_in = pairs_in; a.pairs_out = pairs_out; a.pair_count = pair_count;
   a.kvol = d->kvol; a.pair_cap = d->pair_cap;
+  a.splits = 1; a.k_per = a.n_slabs;
   const int BN = d->Cout > 64 ? 128 : 64;
   a.n_tiles = tt_cdiv(d->Cout, BN);
   CUtensorMap mb_hi, mb_lo;
@@ -779,15 +862,15 @@ int tt_sparse_conv_tc(const tt_sparse_conv_desc* d, const float* feats_in, const
   if (BN == 128) {
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 128 * KS * 4) + 1024 + EPI_BYTES;
     static bool set128 = false;
-    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
+    if (!set128) { cudaFuncSetAttribute(conv_tc_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set128 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, false, true>, mb_hi, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 3, true>, mb_hi, mb_hi, mb_lo, a);
   } else {
     constexpr int smem = 3 * (2 * BM * KS * 4 + 2 * 64 * KS * 4) + 1024 + EPI_BYTES;
     static bool set64 = false;
-    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
+    if (!set64) { cudaFuncSetAttribute(conv_tc_kernel<64, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set64 = true; }
     cfg.dynamicSmemBytes = smem;
-    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, false, true>, mb_hi, mb_hi, mb_lo, a);
+    lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, 3, true>, mb_hi, mb_hi, mb_lo, a);
   }
   if (lerr != cudaSuccess) { tt_set_error("tt_sparse_conv(tc): cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;

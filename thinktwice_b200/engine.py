@@ -184,7 +184,8 @@ class Engine:
                   and x.ld % 4 == 0 and x.coff % 4 == 0 and out.ld % 4 == 0 and out.coff % 4 == 0
                   and (res is None or (res.ld % 4 == 0 and res.coff % 4 == 0)) and (res2 is None or (res2.ld % 4 == 0 and res2.coff % 4 == 0))
                   and x_nstride % 4 == 0 and y_nstride % 4 == 0 and x_hstride % 4 == 0
-                  and d.N * OH * OW >= self.tc_min_rows and pw.Cout >= 32)
+                  and (d.N * OH * OW >= self.tc_min_rows or (d.N * OH * OW >= 128 and pw.KH * pw.KW * pw.Cin >= 2048))   # thin M: only with a long K (split-K)
+                  and pw.Cout >= 32)
         d.impl = impl if use_tc else lib.IMPL_SIMT
         ws = None
         need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # SIMT: split-K partials; tcgen05: 0
