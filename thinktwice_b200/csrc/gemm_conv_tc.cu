@@ -427,6 +427,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int u = 0; u < 8; ++u) {
             float4 h, l;
             split_rn(v[u].x, h.x, l.x); split_rn(v[u].y, h.y, l.y); split_rn(v[u].z, h.z, l.z); split_rn(v[u].w, h.w, l.w);
+            if (p.dbg & 64) {                                  // experiment: lo rounded to nearest TF32 instead of truncated by the MMA
+              float t;
+              split_rn(l.x, l.x, t); split_rn(l.y, l.y, t); split_rn(l.z, l.z, t); split_rn(l.w, l.w, t);
+            }
             sts128(raw + (b0 + u) * 512, h);
             if (p.terms == 3) sts128(raw + A_BYTES + (b0 + u) * 512, l);
           }
@@ -684,7 +688,8 @@ int tt_conv2d_tc(const tt_conv_desc* d, const float* x, const float* w_tc, const
   a.d = *d;
   a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
   a.terms = terms;
-  a.chunk = terms == 3 ? 4 : 16;                              // 4 slabs = K 128: 16 truncating accumulations per chunk
+  a.chunk = terms == 3 ? ((g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2) : 16;   // 2 slabs = K 64: 8 truncating accumulations per chunk (4 slabs are 8% faster
+                                                              // end to end but fail the 1e-3 golden bound on one seed: tools/golden_err.py; debug bit 0x20000)
   a.n_slabs = (d->Cin + KS - 1) / KS;
   a.total_pix = d->N * d->OH * d->OW;
   a.flat = (taps == 1 && d->pad == 0 && d->stride == 1 && xhs == (long long)d->W * d->x_ld && xns == (long long)d->H * xhs) ? 1 : 0;
@@ -826,7 +831,7 @@ int tt_sparse_conv_tc(const tt_sparse_conv_desc* d, const float* feats_in, const
   a.d.act = TT_ACT_NONE;
   a.y = feats_out;
   a.terms = d->impl == 3 ? 3 : 1;
-  a.chunk = a.terms == 3 ? 4 : 16;
+  a.chunk = a.terms == 3 ? ((g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2) : 16;
   a.n_slabs = (d->Cin + KS - 1) / KS;
   a.dbg = g_tt_debug & 0xFF;
   a.gx = feats_in; a.gx_ld = d->in_ld;
