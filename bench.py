@@ -236,6 +236,7 @@ def main():
     torch.cuda.synchronize()
     mk = model.eng.marks
     segments = {mk[i][0]: round(mk[i - 1][1].elapsed_time(mk[i][1]), 3) for i in range(1, len(mk))}
+    eager_step_ms = mk[0][1].elapsed_time(mk[-1][1])             # the same serial eager step the per-launch events come from
     model.eng.marks = None
     conv_ms = sum(a.elapsed_time(b) for (_, _, a, b) in model.eng.prof)
     conv_flops = sum(f for (_, f, _, _) in model.eng.prof)
@@ -244,6 +245,12 @@ def main():
         json.dump([(n, f, a.elapsed_time(b)) for (n, f, a, b) in model.eng.prof], open(args.dump_convs, 'w'))
     model.eng.prof = None
     tensor_peak, hbm_peak, peak_src = load_peaks()
+    traffic, traffic_note = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_tc_full.json')
+    if os.path.exists(tpath):                                    # DRAM bytes per launch from the committed ncu --set full capture
+        tj = json.load(open(tpath))
+        traffic = tj['dram_bytes_per_launch_mean']
+        traffic_note = 'bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches: %s' % (len(tj['launches']), tj['source'])
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
     if rank != 0:
@@ -258,8 +265,10 @@ def main():
                      'd2h_bytes_per_step': B * 6 * 4 * 2 * 4},
                 roofline={'bound': 'tensor', 'kernel': 'conv_igemm (implicit-GEMM conv / linear family)',
                           'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
-                          'traffic': None, 'peak_source': peak_src, 'launches_per_step': n_conv,
-                          'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / (ms / args.steps),
+                          'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src, 'launches_per_step': n_conv,
+                          'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / eager_step_ms,
+                          'share_note': 'per-launch CUDA events of one serial eager step (no graph, no stream overlap); share = '
+                                        'family time / that step',
                           'algorithmic_flops_per_step': conv_flops},
                 segments_ms_serial_eager=segments)
     line['config']['parallelism'] = f'dp{world} (frames sharded, one NCCL all_gather of pred_wp)'
