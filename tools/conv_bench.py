@@ -50,7 +50,7 @@ def main():
             for dbg in (dbg_list if impl > 1 else [0]):
                 L.tt_debug_set(dbg)
                 us = run(eng, x, pw, res, k, stride, pad)
-                line += f' | {tag}{"/d%d" % dbg if dbg else ""} {us:7.1f}us {gf / us * 1e-3 * 1e3:6.1f}TF/s'
+                line += f' | {tag}{"/d%d" % dbg if dbg else ""} {us:7.1f}us {gf / us * 1e3:6.1f}TF/s'
             L.tt_debug_set(0)
         print(line, flush=True)
 
