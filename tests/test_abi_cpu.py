@@ -70,3 +70,31 @@ def test_config_model_section_equals_reference_when_present():
             out.append((path, a, b))
         return out
     assert not diff(norm(ours.model), norm(ref.model))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every descriptor struct as gcc lays out include/tt_b200.h vs. the ctypes mirror in lib.py
+    (the header is plain C99: it must compile without a C++ compiler)."""
+    import ctypes as C
+    import os
+    import subprocess
+    from thinktwice_b200 import lib
+    pairs = {'tt_conv_desc': lib.ConvDesc, 'tt_lift_splat_desc': lib.LiftSplatDesc, 'tt_voxelize_desc': lib.VoxelizeDesc,
+             'tt_rulebook_desc': lib.RulebookDesc, 'tt_sparse_conv_desc': lib.SparseConvDesc, 'tt_look_desc': lib.LookDesc,
+             'tt_msda_desc': lib.MsdaDesc}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "tt_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            src.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ['  return 0;', '}']
+    cfile = tmp_path / 'abi.c'
+    cfile.write_text('\n'.join(src))
+    exe = tmp_path / 'abi'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(root, 'include'), str(cfile), '-o', str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, f'{cname}.{fname}'
