@@ -37,8 +37,12 @@ sys.path.insert(0, HERE)
 def named_init(module, seed, prefix=''):
     """fill every state_dict entry of `module` from a generator seeded by crc32(prefix + name) ^ seed."""
     sd = module.state_dict()
+    params = {n for n, _ in module.named_parameters()} if hasattr(module, 'named_parameters') else None
     out = {}
     for name, t in sd.items():
+        if params is not None and name not in params and not name.endswith(('running_mean', 'running_var')):
+            out[name] = t.clone()                                      # geometry buffers (frustum, voxel_*), step counters: keep
+            continue
         g = torch.Generator().manual_seed((zlib.crc32((prefix + name).encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
         if name.endswith('num_batches_tracked'):
             out[name] = t.clone()
@@ -90,13 +94,97 @@ def load_reference():
     regs['BACKBONES'].classes['LSS'] = _StubEncoder
     regs['BACKBONES'].classes['LidarNet'] = _StubEncoder
     importlib.import_module('olt_code.model_code.dense_heads.thinktwice_decoder')          # registers ThinkTwiceDecoder
-    return importlib.import_module('olt_code.encoder_decoder_framework')
+    return importlib.import_module('olt_code.encoder_decoder_framework'), regs
+
+
+def load_reference_lss(regs):
+    """model_code/backbones/lss.py behind stubs.  Reference-own code exercised: DepthNet / ASPP / Mlp / SELayer / UNet /
+    seg->feature stack / PAFPN forward (the in-tree restatement lss.py:286-348) / create_frustum / get_geometry / the lift /
+    sweep handling / LSS.forward's matrix assembly.  Third-party LEAVES supplied from published semantics (all named in the fixture):
+    mmdet ResNet-50 and PAFPN layer CONSTRUCTION, mmdet BasicBlock, mmcv DCN pack (torchvision deform_conv2d) = oracle.camera.*;
+    ops.voxel_pooling (CUDA-only) = oracle.voxel_pool.voxel_pooling_ref, itself checked against the reference's compiled kernel on
+    the GPU box (tests/test_ops_gpu.py)."""
+    import _ref_stubs
+    from oracle import camera as oc, voxel_pool as ovp
+    for n in ['mmdet.models.backbones', 'mmdet.models.backbones.resnet', 'mmdet.models.necks', 'mmdet.models.necks.pafpn', 'ops',
+              'ops.voxel_pooling']:
+        _ref_stubs._mod(n)
+    S = sys.modules
+
+    class _ResNet(oc.ResNet50):
+        def __init__(self, **cfg):
+            super().__init__()
+
+        def init_weights(self):
+            pass
+
+    class _PAFPNBase(_ref_stubs.BaseModule):                           # mmdet FPN/PAFPN __init__: layer construction only
+        def __init__(self, in_channels, out_channels, num_outs, start_level=0, add_extra_convs=False,
+                     relu_before_extra_convs=False, **kw):
+            super().__init__()
+            n = len(in_channels)
+            self.in_channels, self.out_channels, self.num_outs, self.start_level = in_channels, out_channels, num_outs, start_level
+            self.backbone_end_level, self.add_extra_convs, self.relu_before_extra_convs = n, add_extra_convs, relu_before_extra_convs
+            self.lateral_convs = torch.nn.ModuleList([oc.ConvModule(c, out_channels, 1) for c in in_channels])
+            self.fpn_convs = torch.nn.ModuleList([oc.ConvModule(out_channels, out_channels, 3, padding=1) for _ in range(n)])
+            self.downsample_convs = torch.nn.ModuleList([oc.ConvModule(out_channels, out_channels, 3, stride=2, padding=1) for _ in range(n - 1)])
+            self.pafpn_convs = torch.nn.ModuleList([oc.ConvModule(out_channels, out_channels, 3, padding=1) for _ in range(n - 1)])
+
+        def init_weights(self):
+            pass
+
+    S['mmdet.models'].build_backbone = lambda cfg: _ResNet(**cfg)
+    S['mmdet.models.backbones.resnet'].BasicBlock = lambda cin, cout: oc.BasicBlock(cin)
+    S['mmdet.models.necks.pafpn'].PAFPN = _PAFPNBase
+    S['mmdet3d.models'].build_neck = lambda cfg: regs['NECKS'].build(cfg)
+    S['mmcv.cnn'].build_conv_layer = lambda cfg, *a, **k: oc.DeformConv2dPack(cfg['in_channels'], cfg['out_channels'], cfg['groups'])
+    S['ops.voxel_pooling'].voxel_pooling = ovp.voxel_pooling_ref
+    m = types.ModuleType('olt_code.model_code.backbones')
+    m.__path__ = [REF + '/model_code/backbones']
+    sys.modules['olt_code.model_code.backbones'] = m
+    lss = importlib.import_module('olt_code.model_code.backbones.lss')
+    regs['NECKS'].classes['PAFPN'] = lss.PAFPN_fp32                    # cfg type 'PAFPN' (mmdet's): same forward, restated in-tree
+    return lss
+
+
+def lss_digest(out):
+    """what the fixture keeps of an LSS output dict: small tensors whole, big maps as channel means + a strided sub-grid."""
+    keep = {'bev': out['bev'], 'depth': out['depth'], 'lidar2img': out['lidar2img'], 'ida_mat': out['ida_mat'],
+            'seg.mean_hw': out['seg'].mean((-2, -1)), 'seg.sub8': out['seg'][..., ::8, ::8]}
+    for i, f in enumerate(out['fpn_feats']):
+        keep[f'fpn{i}.mean_hw'] = f.mean((-2, -1))
+        keep[f'fpn{i}.sub'] = f[..., ::4, ::4][:, ::8]
+    return keep
+
+
+def lss_case(regs):
+    """camera encoder at the plumbing shape: reference LSS.forward vs the same inputs, name-keyed weights."""
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    lss = load_reference_lss(regs)
+    kw = {k: v for k, v in dict(cfg.model['img_encoder']).items() if k != 'type'}
+    for seed, B in ((0, 1), (1, 2)):
+        torch.manual_seed(seed)
+        ref = lss.LSS(**kw).eval()
+        named_init(ref, seed, prefix='img_encoder.')
+        batch = make_batch(cfg, B, seed=seed, num_points=10)
+        with torch.no_grad():
+            out = ref(batch['img'], batch['img_metas'], is_return_depth=True)
+        names = sorted(ref.state_dict().keys())
+        keep = lss_digest(out)
+        np.savez_compressed(os.path.join(HERE, f'ref_lss_plumbing_seed{seed}.npz'), batch=np.array(B), names=np.array(names),
+                            shapes=np.array([str(tuple(ref.state_dict()[n].shape)) for n in names]),
+                            **{k: v.detach().cpu().numpy().astype(np.float32) for k, v in keep.items()})
+        print(f'lss seed {seed} B {B}: bev {tuple(out["bev"].shape)} |bev| {float(out["bev"].abs().max()):.3f} seg {tuple(out["seg"].shape)} '
+              f'depth {tuple(out["depth"].shape)}')
 
 
 def main():
     from thinktwice_b200.config import Config, DEFAULT_CONFIG
     cfg = Config.fromfile(DEFAULT_CONFIG)
-    fw = load_reference()
+    fw, regs = load_reference()
+    lss_case(regs)
     mc = cfg.model
     for seed, B in ((0, 1), (1, 1), (2, 2)):                           # B = 2: the Look module couples the frames of a batch (SURVEY fact 4)
         torch.manual_seed(seed)

@@ -75,3 +75,29 @@ def test_product_host_action_and_pid_equal_the_reference_code(seed):
     s2, t2, b2, meta = m.control_pid(pred['pred_wp'][:, -1], x['speed'][:1], tp)
     got = [float(s2), float(t2), float(b2)] + [meta[k] for k in ('desired_speed', 'angle', 'angle_last', 'angle_target', 'angle_final', 'delta')]
     assert np.allclose(got, f['pid'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_oracle_camera_encoder_equals_the_reference_lss(seed):
+    """oracle.camera.LSS vs the reference's model_code/backbones/lss.py (DepthNet, ASPP, UNet, seg->feature, PAFPN forward,
+    frustum / geometry with its quirks, lift, sweep handling) at the plumbing shape; B = 2 in seed 1."""
+    from make_reference_golden import lss_digest, named_init
+    from oracle.camera import LSS
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    f = np.load(os.path.join(G, f'ref_lss_plumbing_seed{seed}.npz'))
+    o = LSS(**{k: v for k, v in dict(cfg.model['img_encoder']).items() if k != 'type'}).eval()
+    sd = o.state_dict()
+    assert sorted(sd) == list(f['names'])                              # same parameter / buffer names as the reference module
+    assert [str(tuple(sd[n].shape)) for n in f['names']] == list(f['shapes'])
+    named_init(o, seed, prefix='img_encoder.')
+    batch = make_batch(cfg, int(f['batch']), seed=seed, num_points=10)
+    with torch.no_grad():
+        keep = {}
+        out = o(batch['img'], batch['img_metas'], keep)
+    out = dict(out)
+    out.setdefault('depth', keep.get('depth'))
+    got = lss_digest(out)
+    for k, v in got.items():
+        assert rel(v.numpy(), f[k]) < 2e-5, k                          # index_add order / conv algorithm choice: not bitwise
