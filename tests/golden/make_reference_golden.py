@@ -91,6 +91,7 @@ def load_reference():
         def __init__(self, d_bound=(1.0, 41.0, 0.5), **kw):
             super().__init__()
             self.d_bound = d_bound
+    regs['stub_encoder'] = _StubEncoder
     regs['BACKBONES'].classes['LSS'] = _StubEncoder
     regs['BACKBONES'].classes['LidarNet'] = _StubEncoder
     importlib.import_module('olt_code.model_code.dense_heads.thinktwice_decoder')          # registers ThinkTwiceDecoder
@@ -186,6 +187,7 @@ def main():
     fw, regs = load_reference()
     lss_case(regs)
     mc = cfg.model
+    regs['BACKBONES'].classes['LSS'] = regs['stub_encoder']            # (importing lss.py registered the real LSS)
     for seed, B in ((0, 1), (1, 1), (2, 2)):                           # B = 2: the Look module couples the frames of a batch
         torch.manual_seed(seed)
         ref = fw.EncoderDecoder(img_encoder=dict(mc['img_encoder']), decoder=dict(mc['decoder']), lidar_encoder=dict(mc['lidar_encoder']),
