@@ -23,7 +23,8 @@ pin comes from running the reference's own code:
     /root/reference behind import stubs and runs them; tests/test_reference_golden_cpu.py checks this oracle against the
     stored outputs: BEV fusion + SE pyramid, the whole ThinkTwiceDecoder (B = 1 and the batch-coupled B = 2), the camera
     encoder LSS.forward at the plumbing shape (DepthNet / ASPP / UNet / seg->feature / PAFPN forward / frustum / geometry
-    / lift / sweeps), process_action / control_pid — bit-exact, and the 607 + 551 state_dict names and shapes identical.
+    / lift / sweeps), EncoderDecoder.forward_inference end to end at the plumbing shape, process_action / control_pid —
+    bit-exact, and the state_dict names and shapes identical.
 (b) PINNED by the reference's own CUDA kernel — voxel pooling, compiled from /root/reference into ``oracle/_ref``
     (oracle/build_ref.py) and run beside the product kernel on the GPU box.
 (c) UNPINNED (third-party code that is not under /root/reference; restated from published semantics and held by

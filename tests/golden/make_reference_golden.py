@@ -181,11 +181,46 @@ def lss_case(regs):
               f'depth {tuple(out["depth"].shape)}')
 
 
+PRED_KEYS = ('pred_wp', 'mu_branches', 'sigma_branches', 'future_mu', 'future_sigma', 'pred_speed', 'pred_value_traj', 'pred_value_ctrl',
+             'refine_flattned_BEV_feature', 'refine_BEV_feature')
+
+
+def e2e_case(fw, regs):
+    """the reference's EncoderDecoder.forward_inference end to end at the plumbing shape (framework:194-250: state assembly,
+    extract_sensor_feat with its rot90(flip), fusion, decoder) with the reference LSS as camera encoder.  The LiDAR encoder is
+    third-party glue over mmdet3d / spconv (lidarnet.py:28-96): oracle.lidar.LidarNet stands in for it on both sides."""
+    from oracle.lidar import LidarNet
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    mc = cfg.model
+    lss = sys.modules['olt_code.model_code.backbones.lss']
+    regs['BACKBONES'].classes['LSS'] = lss.LSS
+    regs['BACKBONES'].classes['LidarNet'] = LidarNet
+    for seed, B in ((0, 1), (1, 2)):
+        torch.manual_seed(seed)
+        ref = fw.EncoderDecoder(img_encoder=dict(mc['img_encoder']), decoder=dict(mc['decoder']), lidar_encoder=dict(mc['lidar_encoder']),
+                                train_cfg=mc['train_cfg'], test_cfg=mc.get('test_cfg')).eval()
+        named_init(ref, seed)
+        batch = make_batch(cfg, B, seed=seed, num_points=1500)
+        batch['target_command_raw'] = batch['target_command'].argmax(-1)
+        with torch.no_grad():
+            pred = ref.forward_inference(batch)
+        names = sorted(ref.state_dict().keys())
+        np.savez_compressed(os.path.join(HERE, f'ref_e2e_plumbing_seed{seed}.npz'), batch=np.array(B), names=np.array(names),
+                            shapes=np.array([str(tuple(ref.state_dict()[n].shape)) for n in names]),
+                            **{k: pred[k].detach().cpu().numpy() for k in PRED_KEYS})
+        print(f'e2e seed {seed} B {B}: pred_wp[-1] = {[round(float(v), 4) for v in pred["pred_wp"][0, -1].flatten()]}')
+    regs['BACKBONES'].classes['LSS'] = regs['stub_encoder']
+    regs['BACKBONES'].classes['LidarNet'] = regs['stub_encoder']
+
+
 def main():
     from thinktwice_b200.config import Config, DEFAULT_CONFIG
     cfg = Config.fromfile(DEFAULT_CONFIG)
     fw, regs = load_reference()
     lss_case(regs)
+    e2e_case(fw, regs)
     mc = cfg.model
     regs['BACKBONES'].classes['LSS'] = regs['stub_encoder']            # (importing lss.py registered the real LSS)
     for seed, B in ((0, 1), (1, 1), (2, 2)):                           # B = 2: the Look module couples the frames of a batch (SURVEY fact 4)

@@ -101,3 +101,25 @@ def test_oracle_camera_encoder_equals_the_reference_lss(seed):
     got = lss_digest(out)
     for k, v in got.items():
         assert rel(v.numpy(), f[k]) < 2e-5, k                          # index_add order / conv algorithm choice: not bitwise
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_oracle_forward_inference_equals_the_reference_end_to_end(seed):
+    """EncoderDecoder.forward_inference at the plumbing shape: reference framework + reference LSS + reference decoder (the LiDAR
+    encoder, third-party glue, is oracle.lidar.LidarNet on both sides) vs the oracle, name-keyed weights; B = 2 in seed 1."""
+    from make_reference_golden import PRED_KEYS, named_init
+    from oracle.model import EncoderDecoder as Oracle
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    f = np.load(os.path.join(G, f'ref_e2e_plumbing_seed{seed}.npz'))
+    o = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'}).eval()
+    sd = o.state_dict()
+    assert sorted(sd) == list(f['names'])                              # the full model: names and shapes as the reference builds them
+    assert [str(tuple(sd[n].shape)) for n in f['names']] == list(f['shapes'])
+    named_init(o, seed)
+    batch = make_batch(cfg, int(f['batch']), seed=seed, num_points=1500)
+    with torch.no_grad():
+        pred = o.forward_inference(batch)
+    for k in PRED_KEYS:
+        assert rel(pred[k].numpy(), f[k]) < 1e-5, k
