@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 
+_REGS = None                                                       # registries of an already-loaded reference (tests reuse it)
+
+
 def named_init(module, seed, prefix=''):
     """fill every state_dict entry of `module` from a generator seeded by crc32(prefix + name) ^ seed."""
     sd = module.state_dict()

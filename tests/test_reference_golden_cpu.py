@@ -123,3 +123,41 @@ def test_oracle_forward_inference_equals_the_reference_end_to_end(seed):
         pred = o.forward_inference(batch)
     for k in PRED_KEYS:
         assert rel(pred[k].numpy(), f[k]) < 1e-5, k
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/open_loop_training/code'), reason='needs the mounted reference tree')
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_committed_plumbing_golden_is_reproduced_by_the_reference_code(seed):
+    """tests/golden/plumbing_seed*.npz (what the GPU suite holds the product to) were generated by the oracle; here the SAME
+    calibrated weights are loaded into the reference's own EncoderDecoder (reference framework + LSS + decoder behind import
+    stubs, state_dict names identical) and its forward_inference must give the stored vectors — so the GPU golden test is,
+    transitively, a test against the reference's code.  Runs only where /root/reference is mounted (the build container)."""
+    import make_reference_golden as mg
+    from oracle.lidar import LidarNet
+    from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    mc = cfg.model
+    if 'olt_code.encoder_decoder_framework' in sys.modules:
+        fw, regs = sys.modules['olt_code.encoder_decoder_framework'], mg._REGS
+    else:
+        fw, regs = mg.load_reference()
+        mg.load_reference_lss(regs)
+        mg._REGS = regs
+    lss = sys.modules['olt_code.model_code.backbones.lss']
+    regs['BACKBONES'].classes['LSS'], regs['BACKBONES'].classes['LidarNet'] = lss.LSS, LidarNet
+    o = Oracle(**{k: v for k, v in mc.items() if k != 'type'})
+    init_oracle_weights(o, seed)
+    batch = make_batch(cfg, 1, seed=seed, num_points=2000)
+    calibrate_bn(o, batch)
+    ref = fw.EncoderDecoder(img_encoder=dict(mc['img_encoder']), decoder=dict(mc['decoder']), lidar_encoder=dict(mc['lidar_encoder']),
+                            train_cfg=mc['train_cfg'], test_cfg=mc.get('test_cfg')).eval()
+    ref.load_state_dict(o.state_dict())                                # strict: identical names and shapes
+    batch['target_command_raw'] = batch['target_command'].argmax(-1)
+    with torch.no_grad():
+        pred = ref.forward_inference(batch)
+    g = np.load(os.path.join(G, f'plumbing_seed{seed}.npz'))
+    for k in ('pred_wp', 'mu_branches', 'sigma_branches', 'future_mu', 'future_sigma', 'pred_speed', 'pred_value_traj',
+              'refine_flattned_BEV_feature'):
+        assert rel(pred[k].numpy(), g[k]) < 1e-5, k
