@@ -1,8 +1,11 @@
 """Generate the committed golden vectors (run once, on CPU):  python tests/golden/make_golden.py
 
-The reference ships no tests or fixtures, so these vectors are produced by the oracle itself
+The reference ships no tests or fixtures, so these vectors are produced by the oracle
 (oracle/ = plain-PyTorch restatement of the reference).  They pin (a) the oracle against accidental edits and
-(b) the B200 path against a stored answer that does not depend on re-running the oracle.
+(b) the B200 path against a stored answer that does not depend on re-running the oracle.  The end-to-end vectors are
+re-derived with the reference's OWN code (same weights loaded into the reference EncoderDecoder behind import stubs) by
+tests/test_reference_golden_cpu.py::test_committed_plumbing_golden_is_reproduced_by_the_reference_code; vectors made
+directly by the reference's code live beside them as ref_*.npz (make_reference_golden.py).
   plumbing_seed{0,1,2}.npz : end-to-end outputs at the plumbing config (weights/inputs regenerated from the seed)
   ops.npz                  : per-op cases with their INPUTS stored (voxel pool, MSDA, hard voxelisation, sparse conv)
 """
