@@ -161,3 +161,37 @@ def test_committed_plumbing_golden_is_reproduced_by_the_reference_code(seed):
     for k in ('pred_wp', 'mu_branches', 'sigma_branches', 'future_mu', 'future_sigma', 'pred_speed', 'pred_value_traj',
               'refine_flattned_BEV_feature'):
         assert rel(pred[k].numpy(), g[k]) < 1e-5, k
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/open_loop_training/code'), reason='needs the mounted reference tree')
+def test_full_thinktwice_config_oracle_equals_the_reference_code():
+    """the bench workload itself (thinktwice.py: 4 cams x 2 sweeps 448x896, 40k LiDAR points, K = 5, B = 1): the reference's
+    EncoderDecoder.forward_inference (its framework, LSS and decoder code; LiDAR encoder = oracle stand-in) against the oracle with
+    the same calibrated weights.  ~70 s of CPU."""
+    import make_reference_golden as mg
+    from oracle.lidar import LidarNet
+    from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
+    from thinktwice_b200.config import Config, DEFAULT_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(DEFAULT_CONFIG)
+    mc = cfg.model
+    if 'olt_code.encoder_decoder_framework' in sys.modules:
+        fw, regs = sys.modules['olt_code.encoder_decoder_framework'], mg._REGS
+    else:
+        fw, regs = mg.load_reference()
+        mg.load_reference_lss(regs)
+        mg._REGS = regs
+    lss = sys.modules['olt_code.model_code.backbones.lss']
+    regs['BACKBONES'].classes['LSS'], regs['BACKBONES'].classes['LidarNet'] = lss.LSS, LidarNet
+    o = Oracle(**{k: v for k, v in mc.items() if k != 'type'})
+    init_oracle_weights(o, 0)
+    batch = make_batch(cfg, 1, seed=0, num_points=40000)
+    calibrate_bn(o, batch)
+    ref = fw.EncoderDecoder(img_encoder=dict(mc['img_encoder']), decoder=dict(mc['decoder']), lidar_encoder=dict(mc['lidar_encoder']),
+                            train_cfg=mc['train_cfg'], test_cfg=mc.get('test_cfg')).eval()
+    ref.load_state_dict(o.state_dict())
+    batch['target_command_raw'] = batch['target_command'].argmax(-1)
+    with torch.no_grad():
+        pr, po = ref.forward_inference(batch), o.forward_inference(batch)
+    for k in mg.PRED_KEYS:
+        assert rel(po[k].numpy(), pr[k].numpy()) < 1e-6, k
