@@ -195,3 +195,61 @@ def test_full_thinktwice_config_oracle_equals_the_reference_code():
         pr, po = ref.forward_inference(batch), o.forward_inference(batch)
     for k in mg.PRED_KEYS:
         assert rel(po[k].numpy(), pr[k].numpy()) < 1e-6, k
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/open_loop_training/code'), reason='needs the mounted reference tree')
+@pytest.mark.parametrize('which', ['plumbing', 'full'])
+def test_product_host_camera_geometry_equals_the_reference_lss(which):
+    """what the PRODUCT computes on the host for the camera branch (thinktwice_b200/lss.py: frustum axes, build_mats, the
+    [ida^-1 | sensor2ego . intrin^-1] pair the lift kernel consumes, DepthNet's 22 camera scalars, the voxel-grid lower bound)
+    against the reference LSS: create_frustum, get_geometry (incl. transpose-not-inverse and key-frame mats for the history
+    sweep) and the tensor DepthNet feeds its BatchNorm1d(22)."""
+    import make_reference_golden as mg
+    from thinktwice_b200.config import Config, DEFAULT_CONFIG, PLUMBING_CONFIG
+    from thinktwice_b200.registry import BACKBONES
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG if which == 'plumbing' else DEFAULT_CONFIG)
+    if 'olt_code.encoder_decoder_framework' not in sys.modules:
+        _, regs = mg.load_reference()
+        mg.load_reference_lss(regs)
+        mg._REGS = regs
+    lss = sys.modules['olt_code.model_code.backbones.lss']
+    kw = {k: v for k, v in dict(cfg.model['img_encoder']).items() if k != 'type'}
+    ref = lss.LSS(**kw).eval()
+    prod = BACKBONES.build(dict(cfg.model['img_encoder']))
+    B = 2
+    batch = make_batch(cfg, B, seed=3, num_points=10)
+    metas = batch['img_metas']
+    N = batch['img'].shape[2]
+    # frustum and grid constants
+    assert torch.equal(prod.frustum(), ref.frustum)
+    assert torch.equal(prod.voxel_coord - prod.voxel_size / 2.0, ref.voxel_coord - ref.voxel_size / 2.0)
+    assert [int(v) for v in prod.voxel_num] == [int(v) for v in ref.voxel_num]
+    # matrices as LSS.forward assembles them (lss.py:667-687)
+    mats = prod.build_mats(metas, N)
+    intr = torch.stack([torch.stack([torch.cat([torch.cat([m['cam_intrinsic'], torch.zeros(N, 3, 1)], 2),
+                                                torch.tensor([0., 0., 0., 1.]).expand(N, 1, 4)], 1) for m in f]) for f in metas])
+    assert torch.equal(mats['intrin_mats'], intr.float())
+    # geometry: reference get_geometry vs the product's two matrices applied the way the lift kernel does
+    T = len(metas[0])
+    fr = prod.frustum()                                                # (D, fH, fW, 4) = (u, v, d, 1)
+    for s in range(T):
+        idx = -1 if s == 0 else -s                                     # the sweep index LSS.forward passes (lss.py:689, 712)
+        geom_ref = ref.get_geometry(mats['sensor2ego_mats'][:, idx], mats['intrin_mats'][:, idx], mats['ida_mats'][:, idx], None)
+        ida_inv = torch.inverse(mats['ida_mats'][:, idx])
+        comb = mats['sensor2ego_mats'][:, idx].matmul(torch.inverse(mats['intrin_mats'][:, idx]))
+        p = torch.einsum('bnij,dhwj->bndhwi', ida_inv, fr)
+        p = torch.cat([p[..., :2] * p[..., 2:3], p[..., 2:]], -1)
+        geom = torch.einsum('bnij,bndhwj->bndhwi', comb, p)[..., :3]
+        assert rel(geom.numpy(), geom_ref.numpy()) < 1e-6
+        # and the integer voxel index, truncation toward zero (lss.py:630-631)
+        lower = ref.voxel_coord - ref.voxel_size / 2.0
+        assert torch.equal(((geom - lower) / ref.voxel_size).int(), ((geom_ref - lower) / ref.voxel_size).int())
+    # DepthNet's camera-awareness vector (lss.py:206-231): capture what reaches BatchNorm1d(22)
+    seen = {}
+    h = ref.depth_net.bn.register_forward_pre_hook(lambda m, inp: seen.setdefault('x', inp[0].detach().clone()))
+    with torch.no_grad():
+        x = torch.zeros(B * N, kw['depth_net_conf']['in_channels'], 2, 2)
+        ref.depth_net(x, {k: v for k, v in mats.items()})
+    h.remove()
+    assert torch.equal(prod.depthnet_mlp_input(mats)[:, :22], seen['x'].reshape(B * N, 22))
