@@ -10,7 +10,7 @@ import torch
 
 from . import lib
 from .engine import FMap
-from .lib import ACT_NONE, ACT_RELU, LiftSplatDesc, _p
+from .lib import ACT_RELU, LiftSplatDesc, _p
 from .registry import BACKBONES
 from .weights import bn_affine
 

@@ -7,7 +7,6 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-import torch
 
 from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
 from thinktwice_b200 import lib
