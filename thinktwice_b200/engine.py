@@ -93,7 +93,7 @@ class Engine:
         self.device = torch.device(device)
         self.impl = impl
         self.bufs = {}
-        self.tc_ws = {}             # per lane: grow-only conv workspace (split-K partial sums of the SIMT kernel)
+        self.conv_ws = {}             # per lane: grow-only conv workspace (split-K partial sums of the SIMT kernel)
         self.lane = 0               # 0 = main stream; 1 = side stream (independent branch running concurrently)
         self._side = None
         self.overlap = True         # run independent branches (side_branch) concurrently
@@ -190,9 +190,9 @@ class Engine:
         ws = None
         need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # SIMT: split-K partials; tcgen05: 0
         if need:
-            ws = self.tc_ws.get(self.lane)
+            ws = self.conv_ws.get(self.lane)
             if ws is None or ws.numel() < need:
-                ws = self.tc_ws[self.lane] = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+                ws = self.conv_ws[self.lane] = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
