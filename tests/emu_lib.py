@@ -281,14 +281,14 @@ class Emu:
     def tt_nchw_to_nhwc(self, x, y, N, Cc, H, W, y_ld, y_coff, cpad, stream):
         self.launches += 1
         src = x.flat()[:N * Cc * H * W].view(N, Cc, H, W)
-        dst = _pix_view(y, N, H, W, y_ld)
+        dst = _pix_view(y, N, H, W, y_ld, C=y_coff + cpad)
         dst[..., y_coff:y_coff + Cc] = src.permute(0, 2, 3, 1)
-        dst[..., y_coff + Cc:y_coff + cpad] = 0
+        dst[..., y_coff + Cc:] = 0
         return 0
 
     def tt_nhwc_to_nchw(self, x, x_ld, x_coff, y, N, Cc, H, W, stream):
         self.launches += 1
-        y.flat()[:N * Cc * H * W].view(N, Cc, H, W).copy_(_pix_view(x, N, H, W, x_ld)[..., x_coff:x_coff + Cc].permute(0, 3, 1, 2))
+        y.flat()[:N * Cc * H * W].view(N, Cc, H, W).copy_(_pix_view(x, N, H, W, x_ld, C=x_coff + Cc)[..., x_coff:].permute(0, 3, 1, 2))
         return 0
 
     def tt_maxpool3x3s2(self, x, y, N, H, W, Cc, stream):
@@ -377,7 +377,7 @@ class Emu:
         from torchvision.ops import deform_conv2d
         self.launches += 1
         xv = _pix_view(x, N, H, W, Cc).permute(0, 3, 1, 2).contiguous()
-        off = _pix_view(offset, N, H, W, off_ld)[..., :18].permute(0, 3, 1, 2).contiguous()
+        off = _pix_view(offset, N, H, W, off_ld, C=18).permute(0, 3, 1, 2).contiguous()
         cg = Cc // groups
         out = torch.zeros(N, H, W, groups, 9, cg)
         eye = torch.zeros(9 * cg, cg, 3, 3)                            # output channel (tap, c) = input channel c sampled at tap
@@ -393,8 +393,8 @@ class Emu:
         d = _desc(d)
         self.launches += 1
         BN = d.B * d.N
-        dl = _pix_view(depth_logits, BN, d.fH, d.fW, d.ld_d)[..., d.d_coff:d.d_coff + d.D].double()
-        cx = _pix_view(context, BN, d.fH, d.fW, d.ld_c)[..., d.c_coff:d.c_coff + d.C].double()
+        dl = _pix_view(depth_logits, BN, d.fH, d.fW, d.ld_d, C=d.d_coff + d.D)[..., d.d_coff:].double()
+        cx = _pix_view(context, BN, d.fH, d.fW, d.ld_c, C=d.c_coff + d.C)[..., d.c_coff:].double()
         prob = dl.softmax(-1)                                          # (BN, fH, fW, D)
         m = mats.flat()[:BN * 32].view(BN, 2, 4, 4)
         u, v, dd = fu.flat()[:d.fW], fv.flat()[:d.fH], fd.flat()[:d.D]
@@ -414,7 +414,7 @@ class Emu:
         out = out.view(d.B, d.Y, d.X, d.C)
         if d.anti_transpose:
             out = out.flip(1).flip(2).transpose(1, 2)
-        _pix_view(bev, d.B, d.Y, d.X, d.bev_ld)[..., d.bev_coff:d.bev_coff + d.C] = out.float()
+        _pix_view(bev, d.B, d.Y, d.X, d.bev_ld, C=d.bev_coff + d.C)[..., d.bev_coff:] = out.float()
         return 0
 
     # ------------------------------------------------------------------ Look module, MSDA

@@ -32,12 +32,15 @@ def emulated(monkeypatch):
     return emu
 
 
-def _pair(cfg_path, B, points, seed, impl):
+def _pair(cfg_path, B, points, seed, impl, sweeps=None):
     from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
     from thinktwice_b200.config import Config
     from thinktwice_b200.registry import build_model
     from thinktwice_b200.synthetic import make_batch
     cfg = Config.fromfile(cfg_path)
+    if sweeps is not None:                                             # plumbing shape with a history sweep (lss.py:710-717)
+        cfg.model['img_encoder']['queue_len'] = sweeps
+        cfg.model['train_cfg']['queue_length'] = sweeps
     o = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'})
     init_oracle_weights(o, seed)
     batch = make_batch(cfg, B, seed=seed, num_points=points)
@@ -48,12 +51,13 @@ def _pair(cfg_path, B, points, seed, impl):
     return o, m, batch
 
 
-@pytest.mark.parametrize('impl,B,seed', [(1, 1, 0), (3, 1, 0), (3, 2, 1)])
-def test_plumbing_forward_through_the_emulated_abi_matches_the_oracle(emulated, impl, B, seed):
+@pytest.mark.parametrize('impl,B,seed,sweeps', [(1, 1, 0, None), (3, 1, 0, None), (3, 2, 1, None), (3, 1, 2, 2)])
+def test_plumbing_forward_through_the_emulated_abi_matches_the_oracle(emulated, impl, B, seed, sweeps):
     """impl 1: SIMT weight layouts; impl 3: the tensor-core layouts (hi / lo planes, row-packed stem, padded thin convs, per-group
-    DCN GEMMs, sparse-conv planes); B = 2 exercises the batch-coupled Look semantics on the product side."""
+    DCN GEMMs, sparse-conv planes); B = 2 exercises the batch-coupled Look semantics on the product side; sweeps = 2 the history
+    sweep (key-frame matrices, no_grad BEV, sweep merge conv)."""
     from thinktwice_b200.config import PLUMBING_CONFIG
-    o, m, batch = _pair(PLUMBING_CONFIG, B, 1500, seed, impl)
+    o, m, batch = _pair(PLUMBING_CONFIG, B, 1500, seed, impl, sweeps)
     keep = {}
     with torch.no_grad():
         ref = o.forward_inference(batch, keep=keep)
