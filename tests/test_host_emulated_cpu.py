@@ -68,3 +68,19 @@ def test_plumbing_forward_through_the_emulated_abi_matches_the_oracle(emulated, 
     assert rel(cam['seg'].nchw(), keep['cam']['seg']) < 5e-4
     assert rel(cam['bev'].nchw(), keep['cam']['bev']) < 5e-4
     assert rel(cam['depth'].nchw().softmax(1), keep['cam_keep']['depth_prob']) < 1e-3
+
+
+def test_full_thinktwice_config_through_the_emulated_abi_matches_the_oracle(emulated):
+    """the bench workload (thinktwice.py: 4 cams x 2 sweeps 448x896, 40k LiDAR points, K = 5, B = 1) with the tensor-core weight
+    layouts: ~1000 emulated launches, ~70 s of CPU."""
+    from thinktwice_b200.config import DEFAULT_CONFIG
+    o, m, batch = _pair(DEFAULT_CONFIG, 1, 40000, 0, 3)
+    keep = {}
+    with torch.no_grad():
+        ref = o.forward_inference(batch, keep=keep)
+    pred = m.forward_inference(batch)
+    for k in ('pred_wp', 'mu_branches', 'sigma_branches', 'future_mu', 'future_sigma', 'pred_speed', 'refine_flattned_BEV_feature'):
+        assert rel(pred[k], ref[k]) < 5e-4, k
+    cam = m.last_cam_feat
+    assert rel(cam['seg'].nchw(), keep['cam']['seg']) < 5e-4
+    assert rel(cam['bev'].nchw(), keep['cam']['bev']) < 5e-4
