@@ -275,5 +275,12 @@ int tt_gru_input(const float* wp, const float* ctrl_sp, int t, int T, float* buf
 
 #ifdef __cplusplus
 }
+/* C++ linkage, mangled exactly like the reference's own definition (ops/voxel_pooling/src/voxel_pooling_forward_cuda.cu:38,
+ * declared at src/voxel_pooling_forward.cpp:21-22): the reference's pybind wrapper links against libtt_b200.so unchanged.
+ * `cudaStream_t` is `struct CUstream_st*`. */
+struct CUstream_st;
+void voxel_pooling_forward_kernel_launcher(int batch_size, int num_points, int num_channels, int num_voxel_x, int num_voxel_y,
+                                           int num_voxel_z, const int* geom_xyz, const float* input_features,
+                                           float* output_features, int* pos_memo, struct CUstream_st* stream);
 #endif
 #endif /* TT_B200_H_ */

@@ -29,6 +29,18 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(L.tt_last_error(), bytes)
 
 
+def test_library_exports_the_reference_launcher_symbol():
+    """the C++ symbol the reference's pybind wrapper calls (ops/voxel_pooling/src/voxel_pooling_forward.cpp:21-22,36):
+    same mangled name as the definition in the reference's own .cu (oracle/_ref carries that one when it was built)."""
+    from thinktwice_b200 import lib
+    L = C.CDLL(lib.LIB_PATH)
+    name = '_Z37voxel_pooling_forward_kernel_launcheriiiiiiPKiPKfPfPiP11CUstream_st'
+    assert hasattr(L, name)
+    ref = os.path.join(ROOT, 'oracle', '_ref', 'libvoxel_pooling_ref.so')
+    if os.path.exists(ref):
+        assert hasattr(C.CDLL(ref), name)                           # the reference build exports the very same symbol
+
+
 def test_product_fails_loudly_without_cuda():
     import pytest
     import torch

@@ -11,27 +11,6 @@ def rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
 
 
-@pytest.fixture
-def emulated(monkeypatch):
-    import emu_lib
-    from thinktwice_b200 import lib
-    emu = emu_lib.Emu()
-    p = emu_lib.make_p()
-    monkeypatch.setattr(lib, 'load', lambda: emu)
-    monkeypatch.setattr(lib, 'require_cuda', lambda dev: None)
-    monkeypatch.setattr(lib, '_p', p)
-    monkeypatch.setattr(lib, '_stream', lambda: None)
-    import thinktwice_b200.engine as engine
-    import thinktwice_b200.lss as lss
-    import thinktwice_b200.lidarnet as lidarnet
-    import thinktwice_b200.thinktwice_decoder as dec
-    import thinktwice_b200.encoder_decoder_framework as fw
-    for mod in (engine, lss, lidarnet, dec, fw):
-        monkeypatch.setattr(mod, '_p', p, raising=False)
-        monkeypatch.setattr(mod, '_stream', lib._stream, raising=False)
-    return emu
-
-
 def _pair(cfg_path, B, points, seed, impl, sweeps=None):
     from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
     from thinktwice_b200.config import Config

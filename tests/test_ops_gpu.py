@@ -205,6 +205,15 @@ def test_voxel_pooling_dropin_matches_oracle_and_reference_kernel(shape):
     assert relerr(out, o2.permute(0, 3, 1, 2)) < 1e-5
     from thinktwice_b200.ops.voxel_pooling import last_pos_memo
     assert torch.equal(last_pos_memo(), memo)                     # integer side: bit-exact
+    # the product's link-level drop-in: the SAME mangled symbol exported by libtt_b200.so (voxel_pooling_forward.cpp:21-22)
+    from thinktwice_b200 import lib as ttlib
+    fn3 = getattr(C.CDLL(ttlib.LIB_PATH), '_Z37voxel_pooling_forward_kernel_launcheriiiiiiPKiPKfPfPiP11CUstream_st')
+    o3 = torch.zeros(B, Y, X, Cc, device='cuda')
+    memo3 = -torch.ones(B, P, 3, dtype=torch.int32, device='cuda')
+    fn3(B, P, Cc, X, Y, 1, C.c_void_p(g.data_ptr()), C.c_void_p(f.data_ptr()), C.c_void_p(o3.data_ptr()),
+        C.c_void_p(memo3.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert relerr(o3, o2) < 1e-5 and torch.equal(memo3, memo)
 
 
 def test_voxel_pooling_empty_input():

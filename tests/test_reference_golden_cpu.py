@@ -222,7 +222,7 @@ def test_product_host_camera_geometry_equals_the_reference_lss(which):
     metas = batch['img_metas']
     N = batch['img'].shape[2]
     # frustum and grid constants
-    assert torch.equal(prod.frustum(), ref.frustum)
+    assert torch.equal(prod.frustum, ref.frustum)
     assert torch.equal(prod.voxel_coord - prod.voxel_size / 2.0, ref.voxel_coord - ref.voxel_size / 2.0)
     assert [int(v) for v in prod.voxel_num] == [int(v) for v in ref.voxel_num]
     # matrices as LSS.forward assembles them (lss.py:667-687)
@@ -232,7 +232,7 @@ def test_product_host_camera_geometry_equals_the_reference_lss(which):
     assert torch.equal(mats['intrin_mats'], intr.float())
     # geometry: reference get_geometry vs the product's two matrices applied the way the lift kernel does
     T = len(metas[0])
-    fr = prod.frustum()                                                # (D, fH, fW, 4) = (u, v, d, 1)
+    fr = prod.frustum                                                  # (D, fH, fW, 4) = (u, v, d, 1)
     for s in range(T):
         idx = -1 if s == 0 else -s                                     # the sweep index LSS.forward passes (lss.py:689, 712)
         geom_ref = ref.get_geometry(mats['sensor2ego_mats'][:, idx], mats['intrin_mats'][:, idx], mats['ida_mats'][:, idx], None)

@@ -298,3 +298,16 @@ int tt_lift_splat(const tt_lift_splat_desc* d, const float* depth_logits, const 
 }
 
 }  // extern "C"
+
+// Link-level drop-in for the reference's launcher: ops/voxel_pooling/src/voxel_pooling_forward.cpp:21-22 declares exactly
+// this C++ symbol and calls it from voxel_pooling_forward_wrapper (:36); the reference defines it in
+// src/voxel_pooling_forward_cuda.cu:38-56.  Building the reference's .cpp against libtt_b200.so instead of its own .cu
+// resolves here.  Same argument list, `void`; unlike the reference (which exit(-1)s on a launch error, :51-54) a failure is
+// reported on stderr and through tt_last_error().
+void voxel_pooling_forward_kernel_launcher(int batch_size, int num_points, int num_channels, int num_voxel_x, int num_voxel_y,
+                                           int num_voxel_z, const int* geom_xyz, const float* input_features,
+                                           float* output_features, int* pos_memo, cudaStream_t stream) {
+  if (tt_voxel_pooling_forward(batch_size, num_points, num_channels, num_voxel_x, num_voxel_y, num_voxel_z, geom_xyz,
+                               input_features, output_features, pos_memo, nullptr, (tt_stream_t)stream) != TT_OK)
+    fprintf(stderr, "voxel_pooling_forward_kernel_launcher: %s\n", tt_last_error());
+}

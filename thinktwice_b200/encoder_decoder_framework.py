@@ -20,6 +20,9 @@ from .weights import Packer, bn_affine
 from . import lss as _lss, lidarnet as _lidarnet, thinktwice_decoder as _decoder  # noqa: F401  (registers the modules)
 
 
+POINT_BUCKET = 8192
+
+
 class PIDController:
     """code/utils.py:7-29 (host-side, stateful)."""
 
@@ -41,6 +44,17 @@ class PIDController:
         return self._K_P * error + self._K_I * integral + self._K_D * derivative
 
 
+def _adopt(host, tree):
+    """move the parameters / buffers / sub-modules of a ParamTree node into `host` (an nn.Module op object)."""
+    for n, m in list(tree._modules.items()):
+        host.add_module(n, m)
+    for n, p in list(tree._parameters.items()):
+        host.register_parameter(n, p)
+    for n, b in list(tree._buffers.items()):
+        if n not in host._buffers:                                 # geometry buffers are computed by the host itself
+            host.register_buffer(n, b)
+
+
 @DETECTORS.register_module()
 class EncoderDecoder(nn.Module):
     def __init__(self, img_encoder, decoder, lidar_encoder=None, num_cams=4, use_depth=False, use_seg=False,
@@ -51,24 +65,29 @@ class EncoderDecoder(nn.Module):
         self.model_cfg = dict(img_encoder=img_encoder, decoder=decoder, lidar_encoder=lidar_encoder)
         self.turn_controller = PIDController(K_P=train_cfg['turn_KP'], K_I=train_cfg['turn_KI'], K_D=train_cfg['turn_KD'], n=train_cfg['turn_n'])
         self.speed_controller = PIDController(K_P=train_cfg['speed_KP'], K_I=train_cfg['speed_KI'], K_D=train_cfg['speed_KD'], n=train_cfg['speed_n'])
+        if lidar_encoder is None:
+            # the reference signature defaults lidar_encoder=None, but its own forward cannot run that way
+            # (framework:55 builds it, :246 calls it, :214 indexes its output unconditionally)
+            raise ValueError('EncoderDecoder needs a lidar_encoder config (the reference forward path requires it)')
         self.img_encoder = build_backbone(img_encoder)
         self.lidar_encoder = build_backbone(lidar_encoder)
         self.decoder = build_head(decoder)
         self.dbound = self.img_encoder.d_bound
-        # parameters / buffers in the reference's state_dict naming (checkpoint-compatible)
-        self.params = ParamTree(param_spec(self.model_cfg), seed=seed)
-        for k, v in self.img_encoder.buffers().items():
-            getattr(self.params.img_encoder, k).copy_(v)
+        # Parameters / buffers under the reference's module paths: the three sub-networks own their
+        # sub-trees, the fusion / pyramid / measurement layers hang off this module directly — exactly the layout
+        # mmcv.runner.load_checkpoint walks (recursive `_load_from_state_dict` over `_modules`, thinktwice_agent.py:170).
+        tree = ParamTree(param_spec(self.model_cfg), seed=seed)
+        for name, child in list(tree._modules.items()):
+            if name in ('img_encoder', 'lidar_encoder', 'decoder'):
+                _adopt(getattr(self, name), child)
+            else:
+                self.add_module(name, child)
         self.eng = None
 
-    # state_dict of the model == state_dict of the parameter tree (reference key names, no prefix)
-    def state_dict(self, *a, **k):
-        return self.params.state_dict(*a, **k)
-
-    def load_state_dict(self, sd, strict=True):
-        r = self.params.load_state_dict(sd, strict=strict)
-        self.eng = None                                            # weights must be re-packed
-        return r
+    def _load_from_state_dict(self, *a, **k):
+        # called by torch's load_state_dict AND by mmcv's recursive loader: any (re)load invalidates the packed weights
+        self.eng = None
+        return super()._load_from_state_dict(*a, **k)
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, device='cuda:0', impl=lib.IMPL_AUTO):
@@ -77,7 +96,7 @@ class EncoderDecoder(nn.Module):
         if impl == lib.IMPL_AUTO:
             impl = lib.IMPL_3XTF32                                  # default engine: tcgen05 3xTF32 (fp32-class)
         self.eng = e = Engine(dev, impl)
-        pk = Packer(self.params.state_dict(), dev, tc_mode=impl if impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) else 0)
+        pk = Packer(self.state_dict(), dev, tc_mode=impl if impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) else 0)
         self.img_encoder.prepare(pk, e)
         self.lidar_encoder.prepare(pk, e)
         self.decoder.prepare(pk, e, self)
@@ -141,11 +160,25 @@ class EncoderDecoder(nn.Module):
         speed = batch['speed'].to(dtype=torch.float32).view(-1, 1) / 12.
         st = torch.cat([speed, batch['target_point'].to(torch.float32), batch['target_command'].to(torch.float32)], -1)
         e.upload('in.state', torch.cat([st, st.new_zeros(B, 3)], 1).contiguous())      # 9 -> 12 columns (vector loads)
-        e.upload('in.img', img)
-        e.upload('in.points', batch['points'][:, -1].contiguous())
+        e.upload('in.img', img.to(torch.float32))
+        # LiDAR points: the point count changes every tick in closed loop (thinktwice_agent.py:340-352).  The cloud is
+        # staged into a buffer whose capacity is the count rounded up to POINT_BUCKET, the tail filled with
+        # out-of-range points (dropped by the voxeliser exactly like any point outside point_cloud_range), so that one
+        # arena and one CUDA graph serve every tick of a bucket.
+        pts = batch['points'][:, -1].to(torch.float32)
+        P = pts.shape[1]
+        cap = -(-P // POINT_BUCKET) * POINT_BUCKET
+        mv = self.lidar_encoder.max_voxels
+        if cap > mv >= P:                                          # tt_voxelize_mean wants points per frame <= max_voxels
+            cap = mv
+        pb = e.buf('in.points', (B, cap, pts.shape[2]))
+        if cap != P:
+            e.fill(pb, 1e30)
+        pb[:, :P].copy_(pts, non_blocking=True)
+        e.cur['in.points'] = pb
         lidar2img, ida = self.img_encoder.stage(batch['img_metas'], B, T, N)
         self.decoder.stage(lidar2img, ida)
-        return (B, T, N, tuple(img.shape), tuple(batch['points'].shape))
+        return (B, T, N, tuple(img.shape), cap)
 
     def _device_forward(self):
         """Device half: extract_sensor_feat (framework:238-250) + get_fusion_feat + decoder, kernels only."""
@@ -196,8 +229,20 @@ class EncoderDecoder(nn.Module):
         g[0].replay()
         return g[1].fresh()
 
-    def forward(self, is_eval=True, **kwargs):
-        raise NotImplementedError('training / loss path is out of scope (SURVEY.md §8f f4); use forward_inference')
+    def forward(self, is_eval=True, return_loss=False, **kwargs):
+        """Reference signature (framework:393-407: `forward(is_eval=True, **kwargs)` with the batch as keywords).
+        The reference body always evaluates the training losses (`forward_train` + `_parse_losses`); losses and their
+        teacher-forcing inputs are out of this path's scope.  What IS on the path — the network forward
+        over the batch — runs here: the keywords are taken as the batch dict of `forward_inference`, and the result comes
+        back in the reference's output dict shape with the predictions attached and no loss."""
+        if return_loss:
+            raise NotImplementedError('losses / teacher forcing belong to the training path (SURVEY.md §8f f4)')
+        pred = self.forward_inference(kwargs)
+        return dict(loss=None, log_vars={}, num_samples=kwargs['img'].shape[0], pred=pred)
+
+    def forward_test(self, **kwargs):
+        """mmdet-style test entry: the batch as keywords -> pred dict."""
+        return self.forward_inference(kwargs)
 
     # ------------------------------------------------------------------ host post-processing (framework:268-390)
     @staticmethod

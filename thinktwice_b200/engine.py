@@ -93,7 +93,9 @@ class Engine:
         self.device = torch.device(device)
         self.impl = impl
         self.bufs = {}
+        self.cur = {}                 # name -> the buffer the latest upload(name, ...) went to (shape-keyed arena: see static())
         self.conv_ws = {}             # per lane: grow-only conv workspace (split-K partial sums of the SIMT kernel)
+        self._ws_retired = []         # outgrown workspaces stay alive: CUDA graphs captured earlier still point at them
         self.lane = 0               # 0 = main stream; 1 = side stream (independent branch running concurrently)
         self._side = None
         self.overlap = True         # run independent branches (side_branch) concurrently
@@ -130,13 +132,16 @@ class Engine:
         """copy a host (or device) tensor into the persistent device buffer `name` (static address: graph-safe)."""
         b = self.buf(name, t.shape, t.dtype)
         b.copy_(t, non_blocking=True)
+        self.cur[name] = b
         return b
 
     def static(self, name):
-        for (n, _, _), t in self.bufs.items():
-            if n == name:
-                return t
-        raise KeyError(f'static buffer {name} has not been staged')
+        """the buffer of the LATEST upload under `name`.  Buffers are keyed by (name, shape, dtype), so when an input
+        changes shape between forwards (batch size, LiDAR point count) a stale sibling of the same name exists too."""
+        try:
+            return self.cur[name]
+        except KeyError:
+            raise KeyError(f'static buffer {name} has not been staged') from None
 
     def fmap(self, name, N, H, W, C, ld=None, zero=False):
         ld = ld if ld is not None else C
@@ -192,6 +197,8 @@ class Engine:
         if need:
             ws = self.conv_ws.get(self.lane)
             if ws is None or ws.numel() < need:
+                if ws is not None:
+                    self._ws_retired.append(ws)
                 ws = self.conv_ws[self.lane] = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -9,6 +9,7 @@ at lidarnet.py:90 `coors[-1, 0] + 1`).
 import ctypes as C
 
 import torch
+import torch.nn as nn
 
 from . import lib
 from .lib import ACT_RELU, RulebookDesc, VoxelizeDesc, _p
@@ -38,10 +39,11 @@ def _t3(v):
 
 
 @BACKBONES.register_module()
-class LidarNet:
+class LidarNet(nn.Module):
     def __init__(self, bev_h=None, bev_w=None, pts_voxel_layer=None, pts_voxel_encoder=None, pts_middle_encoder=None,
                  pts_fusion_layer=None, pts_backbone=None, pts_neck=None, pts_bbox_head=None, train_cfg=None,
                  test_cfg=None, prefix='lidar_encoder.'):
+        super().__init__()
         self.prefix = prefix
         self.vcfg = dict(pts_voxel_layer)
         self.num_features = pts_voxel_encoder['num_features']
@@ -51,6 +53,8 @@ class LidarNet:
         vs = np.asarray(self.vcfg['voxel_size'], np.float32)
         r = np.asarray(self.vcfg['point_cloud_range'], np.float32)
         self.grid = [int(v) for v in np.round((r[3:] - r[:3]) / vs)]          # (x, y, z)
+        mv = self.vcfg['max_voxels']
+        self.max_voxels = int(mv[1] if isinstance(mv, (list, tuple)) else mv)     # (train, eval) pair: eval
 
     def prepare(self, pk, eng):
         self.eng = eng
@@ -117,8 +121,7 @@ class LidarNet:
         d.lower, d.vsize = lib.f3(v['point_cloud_range'][:3]), lib.f3(v['voxel_size'])
         d.grid = lib.i3(self.grid)
         d.zmax = self.me.sparse_shape[0]
-        mv = v['max_voxels']
-        d.max_points, d.max_voxels = v['max_num_points'], (mv[1] if isinstance(mv, (list, tuple)) else mv)
+        d.max_points, d.max_voxels = v['max_num_points'], self.max_voxels
         cap = B * P
         d.cap = cap
         ws = e.buf('vox.ws', (lib.load().tt_voxelize_workspace_bytes(C.byref(d)),), dtype=torch.uint8)
@@ -177,4 +180,3 @@ class LidarNet:
             off += co
         return [e.anti_transpose(cat, 'lidar.out.at')]                # framework:246 rot90(flip)
 
-    __call__ = forward

@@ -7,6 +7,7 @@ math runs in libtt_b200 (channels-last, BN folded, concat by channel offset, fus
 import ctypes as C
 
 import torch
+import torch.nn as nn
 
 from . import lib
 from .engine import FMap
@@ -16,18 +17,22 @@ from .weights import bn_affine
 
 
 @BACKBONES.register_module()
-class LSS:
+class LSS(nn.Module):
+    """nn.Module so that the reference-named parameters ('img_encoder.img_backbone.conv1.weight', ...) live in THIS
+    module's tree: mmcv's recursive checkpoint loader (thinktwice_agent.py:170) finds them by walking `_modules`."""
+
     def __init__(self, x_bound, y_bound, z_bound, d_bound, final_dim, downsample_factor, output_channels,
                  img_backbone_conf=None, img_neck_conf=None, depth_net_conf=None, seg_net_conf=None, queue_len=1,
                  fpn_in_channels=(256, 256, 256, 256), prefix='img_encoder.'):
+        super().__init__()
         self.prefix = prefix
         self.d_bound, self.final_dim = list(d_bound), tuple(final_dim)
         self.downsample_factor, self.output_channels, self.queue_len = downsample_factor, output_channels, queue_len
         rows = [x_bound, y_bound, z_bound]
         # buffers exactly as lss.py:386-398 (fp32 arithmetic of the reference)
-        self.voxel_size = torch.Tensor([r[2] for r in rows])
-        self.voxel_coord = torch.Tensor([r[0] + r[2] / 2.0 for r in rows])
-        self.voxel_num = torch.LongTensor([(r[1] - r[0]) / r[2] for r in rows])
+        self.register_buffer('voxel_size', torch.Tensor([r[2] for r in rows]))
+        self.register_buffer('voxel_coord', torch.Tensor([r[0] + r[2] / 2.0 for r in rows]))
+        self.register_buffer('voxel_num', torch.LongTensor([(r[1] - r[0]) / r[2] for r in rows]))
         self.fH, self.fW = final_dim[0] // downsample_factor, final_dim[1] // downsample_factor
         self.frustum_d = torch.arange(*d_bound, dtype=torch.float)
         self.frustum_u = torch.linspace(0, final_dim[1] - 1, self.fW, dtype=torch.float)
@@ -35,15 +40,12 @@ class LSS:
         self.depth_channels = self.frustum_d.numel()
         self.mid = depth_net_conf['mid_channels']
         self.n_seg = seg_net_conf['out_channels']
+        self.register_buffer('frustum', self.make_frustum())
 
-    def frustum(self):
+    def make_frustum(self):
         D, fH, fW = self.depth_channels, self.fH, self.fW
         return torch.stack((self.frustum_u.view(1, 1, fW).expand(D, fH, fW), self.frustum_v.view(1, fH, 1).expand(D, fH, fW),
                             self.frustum_d.view(D, 1, 1).expand(D, fH, fW), torch.ones(D, fH, fW)), -1)
-
-    def buffers(self):
-        return {'voxel_size': self.voxel_size, 'voxel_coord': self.voxel_coord, 'voxel_num': self.voxel_num,
-                'frustum': self.frustum()}
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, pk, eng):
@@ -99,7 +101,9 @@ class LSS:
         dev = eng.device
         self.fu, self.fv, self.fd = self.frustum_u.to(dev), self.frustum_v.to(dev), self.frustum_d.to(dev)
         # lower bound of the voxel grid exactly as lss.py:630 evaluates it in fp32
-        self.lower = (self.voxel_coord - self.voxel_size / 2.0)
+        # host copies of the (checkpoint-loadable) geometry buffers: the forward never reads a device scalar back
+        self.h_vsize, self.h_vnum = self.voxel_size.float().cpu(), [int(v) for v in self.voxel_num.cpu()]
+        self.lower = (self.voxel_coord.float().cpu() - self.h_vsize / 2.0)
 
     # ------------------------------------------------------------------ host-side matrices (lss.py:667-687, 496-502)
     @staticmethod
@@ -251,8 +255,8 @@ class LSS:
         d = LiftSplatDesc()
         d.B, d.N, d.D, d.fH, d.fW, d.C = B, N, self.depth_channels, src.H, src.W, self.output_channels
         d.ld_d, d.d_coff, d.ld_c, d.c_coff = depth.ld, 0, feat.ld, 0
-        d.lower, d.size = lib.f3(self.lower), lib.f3(self.voxel_size)
-        d.X, d.Y, d.Z = (int(v) for v in self.voxel_num)
+        d.lower, d.size = lib.f3(self.lower), lib.f3(self.h_vsize)
+        d.X, d.Y, d.Z = self.h_vnum
         d.bev_ld, d.bev_coff, d.anti_transpose = bev_out.ld, 0, 0
         ws = e.buf('lift.ws', (lib.load().tt_lift_splat_workspace_bytes(C.byref(d)),), dtype=torch.uint8)
         lib.call('tt_lift_splat', C.byref(d), _p(depth.t), _p(feat.t), _p(m), _p(self.fu), _p(self.fv), _p(self.fd),
@@ -279,7 +283,7 @@ class LSS:
         e = self.eng
         B, T, N = img.shape[:3]
         assert T == self.queue_len, 'LSS.queue_len must be set correctly in config!'
-        X, Y = int(self.voxel_num[0]), int(self.voxel_num[1])
+        X, Y = self.h_vnum[0], self.h_vnum[1]
         bev_cat = e.fmap('bev_cat', B, Y, X, self.output_channels * T)
         # history sweeps first (their buffers are recycled), key frame last so its FPN maps stay live.
         # bev_feature_list = [key, sweep 1, ...] (lss.py:697,717)
@@ -297,5 +301,3 @@ class LSS:
         outs = self.forward_device(img.to(self.eng.device))
         outs['lidar2img'], outs['ida_mat'] = lidar2img, ida
         return outs
-
-    __call__ = forward

@@ -10,6 +10,7 @@ B" (msda:338-342).  Dead work is skipped with identical outputs: PredictionModul
 import ctypes as C
 
 import torch
+import torch.nn as nn
 
 from . import lib
 from .engine import FMap
@@ -52,9 +53,10 @@ class LazyPred(dict):
 
 
 @HEADS.register_module()
-class ThinkTwiceDecoder:
+class ThinkTwiceDecoder(nn.Module):
     def __init__(self, *args, config=None, bev_h=None, bev_w=None, BEV_feat_dim=256, flattened_BEV_feat_dim=256,
                  prefix='decoder.', **kwargs):
+        super().__init__()
         self.config, self.bev_h, self.bev_w, self.prefix = config, bev_h, bev_w, prefix
         self.T = config['pred_len']
         self.K = config['refine_num']
@@ -265,8 +267,6 @@ class ThinkTwiceDecoder:
         o.lazy('refine_future_BEV_feature', lambda: torch.stack(
             [f.nchw().reshape(B, T, 32, H, W) for f in s_fut], 1).reshape(B, T, K, 32, H, W).transpose(1, 2))  # quirky view (:481)
         return o
-
-    __call__ = forward
 
     def _look_meta(self, B, mlvl):
         e = self.eng
