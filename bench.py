@@ -25,8 +25,18 @@ sys.path.insert(0, ROOT)
 
 METRIC = json.load(open(os.path.join(ROOT, 'BASELINE.json')))['metric'] if os.path.exists(os.path.join(ROOT, 'BASELINE.json')) else \
     'frames/sec full encoder+decoder fwd (4-cam+LiDAR, 200\u00d7200 BEV) at 1/2/4/8 B200'
-WORKLOAD = ('configs[1]: thinktwice.py config, 4 cams x 2 sweeps 448x896 + 40k-point LiDAR, K=5 decoder, batch 1 per GPU '
-            '(the config file yields a 21x21 camera BEV / 84x84 LiDAR BEV, not 200x200: SURVEY.md fact 3)')
+SHAPE = ('thinktwice.py config, 4 cams x 2 sweeps 448x896 + 40k-point LiDAR, K=5 decoder '
+         '(the config file yields a 21x21 camera BEV / 84x84 LiDAR BEV, not 200x200: SURVEY.md fact 3)')
+
+
+def workload(batch, world):
+    """BASELINE.json configs[] entry this run measures."""
+    if batch == 1:
+        return f'configs[1]: {SHAPE}, batch 1 per GPU'
+    if world == 1:
+        return f'configs[2]: {SHAPE}, batch {batch} synthetic frames in one forward, 1 GPU (throughput mode)'
+    return (f'configs[3]: {SHAPE}, batch {batch * world} synthetic frames sharded data-parallel over {world} GPUs '
+            f'({batch} per GPU per forward), one NCCL gather of the waypoints')
 # SURVEY.md §8d: dense MACs per frame (camera 1127.7 G + LiDAR dense 13.7 G + fusion 4.25 G + decoder 63.3 G)
 ALGO_FLOPS_PER_FRAME = 2 * 1.209e12
 
@@ -129,9 +139,10 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=1, help='frames per GPU per step')
+    ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step (32 = the throughput configs[2] / configs[3])')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-worker'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-latency', action='store_true', help='skip the extra B=1 latency measurement')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
     ap.add_argument('--dump-convs', default=None, help='write per-conv-launch (name, flops, ms) of one step to this JSON file')
     ap.add_argument('--conv', default='3xtf32', choices=['simt', '3xtf32', 'tf32'],
@@ -149,8 +160,10 @@ def main():
     cfg = Config.fromfile(DEFAULT_CONFIG)
     base = {'metric': METRIC, 'unit': 'frames/s', 'n_gpus': args.gpus, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'data': 'synthetic (seeded N(0,1) images, synthetic LiDAR, random-init weights)',
-            'config': {'workload': WORKLOAD, 'frames_per_gpu_per_step': args.batch, 'refine_num': 5, 'conv_engine': args.conv, 'cuda_graph': not args.no_graph,
-                       'l2': 'per-step working set (0.5 GB weights + >1 GB activations) exceeds the 126 MB L2; no explicit flush'}}
+            'config': {'workload': workload(args.batch, args.gpus), 'frames_per_gpu_per_step': args.batch, 'global_batch': args.batch * args.gpus,
+                       'refine_num': 5, 'conv_engine': args.conv, 'cuda_graph': not args.no_graph,
+                       'parallelism': f'dp{args.gpus} (frames sharded, one NCCL all_gather of pred_wp)',
+                       'l2': 'per-step working set (0.5 GB weights + >1 GB activations per frame) exceeds the 126 MB L2; no explicit flush'}}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -159,7 +172,8 @@ def main():
         line = dict(base, impl='reference', value=fps, steps=n, warmup=1, ms_per_step=1000.0 / fps, dtype='f32',
                     n_gpus=args.gpus, gpu_launches=0,
                     cpu_baseline={'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                                  'sample': f'{n} full thinktwice.py frames (B=1), oracle incl. dead LiDAR-look / ffn work' + note},
+                                  'sample': f'each step = ONE frame of the {args.batch}-frame batch run through the CPU oracle as a B=1 forward '
+                                            f'(a full batch takes minutes per step); {n} frames timed, oracle incl. dead LiDAR-look / ffn work' + note},
                     e2e={'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
         print(json.dumps(line))
         return
@@ -229,9 +243,15 @@ def main():
     ms_e2e = timed(host, args.steps, read_back=True)
     stop.set(); th.join(timeout=2)
 
+    # ---- the timed execution mode (graph replay + side stream) must reproduce the plain eager launch sequence
+    wp_timed = step(resident).float().cpu().clone()
+    model.use_graph = False
+    wp_eager = step(resident).float().cpu()
+    parity = float((wp_timed - wp_eager).abs().max() / wp_eager.abs().max().clamp_min(1e-12))
+    assert parity < 1e-3 and bool(torch.isfinite(wp_timed).all()), f'graph replay differs from the eager forward: {parity}'
+
     # ---- roofline of the dominant kernel family (implicit-GEMM conv): per-launch CUDA events on the launching stream
-    model.use_graph = False                                      # per-launch events need eager launches
-    model.eng.prof, model.eng.marks = [], []
+    model.eng.prof, model.eng.marks = [], []                     # per-launch events need eager, serial launches
     step(resident)
     torch.cuda.synchronize()
     mk = model.eng.marks
@@ -253,6 +273,24 @@ def main():
         traffic_note = 'bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches: %s' % (len(tj['launches']), tj['source'])
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
+    # ---- closed-loop latency (configs[1]): one frame per forward through the same model, graph replay
+    lat = None
+    if B != 1 and not args.no_latency:
+        host1 = make_batch(cfg, 1, seed=100 + rank)
+        res1 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host1.items()}
+        if not args.no_graph:
+            model.use_graph = True
+        for _ in range(4):
+            model.forward_inference(res1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            model.forward_inference(res1)
+        e1.record()
+        torch.cuda.synchronize()
+        lat = e0.elapsed_time(e1) / 20
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -269,9 +307,14 @@ def main():
                           'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / eager_step_ms,
                           'share_note': 'per-launch CUDA events of one serial eager step (no graph, no stream overlap); share = '
                                         'family time / that step',
-                          'algorithmic_flops_per_step': conv_flops},
-                segments_ms_serial_eager=segments)
-    line['config']['parallelism'] = f'dp{world} (frames sharded, one NCCL all_gather of pred_wp)'
+                          'algorithmic_flops_per_step': conv_flops,
+                          'frac_lower_bound': conv_flops / (ms / args.steps * 1e-3) / 1e12 / tensor_peak,
+                          'lower_bound_note': 'family FLOPs / the WHOLE timed (graph-replayed) step: what the family achieves at least'},
+                segments_ms_serial_eager=segments,
+                checks={'timed_mode_vs_eager_pred_wp_relerr': parity})
+    if lat is not None:
+        line['latency_b1'] = {'ms_per_frame': lat, 'frames_per_s': 1000.0 / lat,
+                              'note': 'configs[1]: one frame per forward (closed-loop mode), same model, CUDA-graph replay, inputs resident'}
     if not args.no_cpu_baseline and args.gpus == 1:
         fps, n, cores, note = cpu_oracle(2, budget_s=90.0)
         line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',

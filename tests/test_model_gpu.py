@@ -48,7 +48,7 @@ def compare_all(oracle, model, batch, tol=TOL):
     errs['seg'] = relerr(cam['seg'].nchw(), keep['cam']['seg'])
     errs['img_feature'] = relerr(cam['img_feature'].nchw(), keep['cam_keep']['img_feature'])
     errs['cam_bev'] = relerr(cam['bev'].nchw(), keep['cam']['bev'])
-    errs['lidar_bev'] = relerr(model.eng.bufs[[k for k in model.eng.bufs if k[0] == 'lidar.out.at'][0]].permute(0, 3, 1, 2), keep['lidar'][0])
+    errs['lidar_bev'] = relerr(model.eng.static_named('lidar.out.at').permute(0, 3, 1, 2), keep['lidar'][0])
     for k in ('bev_feature', 'pred_speed', 'pred_features_traj', 'pred_wp', 'mu_branches', 'sigma_branches', 'future_mu',
               'future_sigma', 'refine_flattned_BEV_feature', 'refine_BEV_feature', 'refine_future_BEV_feature'):
         errs[k] = relerr(pred[k], ref[k])
@@ -81,9 +81,9 @@ def test_repeat_forward_is_bitwise_stable_where_deterministic():
     assert float((a - b).abs().max()) < 1e-4 * float(a.abs().max())
 
 
-@pytest.mark.parametrize('K', [2, 3])
+@pytest.mark.parametrize('K', [2, 3, 10])
 def test_decoder_depth_sweep_matches_oracle(K):
-    """BASELINE.json configs[4] (K in {1,2,3,5,10}): K=1 and K=5 are the plumbing / full configs, here K=2,3."""
+    """BASELINE.json configs[4] (K in {1,2,3,5,10}): K=1 and K=5 are the plumbing / full configs, here K=2,3,10."""
     from thinktwice_b200.config import PLUMBING_CONFIG
     _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 1000, seed=3, impl=3, refine_num=K)
     errs = compare_all(oracle, model, batch)
@@ -106,9 +106,87 @@ def test_cuda_graph_replay_equals_eager():
     assert relerr(p2, model.forward_inference(other)['pred_wp']) < 1e-4
 
 
-def test_full_thinktwice_config_b1_matches_oracle():
-    """BASELINE.json configs[1]: thinktwice.py, 4 cams x 2 sweeps 448x896 + 40k LiDAR points, K=5, batch 1."""
+@pytest.fixture(scope='module')
+def full():
+    """the thinktwice.py model pair (oracle + product, tensor-core engine), built once for the full-shape tests."""
     from thinktwice_b200.config import DEFAULT_CONFIG
-    _, oracle, model, batch = build_pair(DEFAULT_CONFIG, 1, 40000, impl=3)
-    compare_all(oracle, model, batch)
+    cfg, oracle, model, batch = build_pair(DEFAULT_CONFIG, 1, 40000, impl=3)
+    return dict(cfg=cfg, oracle=oracle, model=model, batch=batch)
 
+
+def test_full_thinktwice_config_b1_matches_oracle(full):
+    """BASELINE.json configs[1]: thinktwice.py, 4 cams x 2 sweeps 448x896 + 40k LiDAR points, K=5, batch 1."""
+    full['model'].use_graph = False
+    full['errs_b1'] = compare_all(full['oracle'], full['model'], full['batch'])
+
+
+def test_full_config_graph_replay_matches_oracle_and_eager(full):
+    """the BENCHMARKED execution mode (bench.py: CUDA-graph replay, LiDAR encoder on a side stream) at the full shape:
+    graph replay vs the oracle (1e-3) and vs the eager launch sequence (red.add accumulation order differs: 1e-4)."""
+    model, batch = full['model'], full['batch']
+    model.use_graph = False
+    eager = {k: model.forward_inference(batch)[k].clone() for k in ('pred_wp', 'mu_branches', 'sigma_branches', 'refine_BEV_feature')}
+    model.enable_cuda_graph()
+    try:
+        for _ in range(3):                                          # warm-up + capture, then pure replays
+            model.forward_inference(batch)
+        compare_all(full['oracle'], model, batch)                   # forward_inference inside = a graph replay
+        pred = model.forward_inference(batch)
+        for k, v in eager.items():
+            assert relerr(pred[k], v) < 1e-4, k
+    finally:
+        model.use_graph = False
+
+
+def test_full_config_b2_with_collate_padding_matches_oracle(full):
+    """B = 2 at the full shape (batch-coupled Look semantics, msda:338-342) with unequal clouds: frame 1 has 31k real
+    points, zero-padded to 40k the way mmcv's collate pads (SURVEY A9 hazard: the zeros ARE points, they land in one voxel)."""
+    from thinktwice_b200.synthetic import make_batch
+    batch = make_batch(full['cfg'], 2, seed=11, num_points=40000)
+    batch['points'][1, :, 31000:] = 0
+    full['model'].use_graph = False
+    compare_all(full['oracle'], full['model'], batch)
+
+
+def test_throughput_config_b32_encoder_is_batch_invariant_and_decoder_matches_oracle(full):
+    """BASELINE.json configs[2] (and the per-GPU shard of configs[3]): 32 frames in one forward.
+    The CPU oracle needs ~10 s per frame, so the batch is checked in two parts, both at B = 32:
+      * encoder (per-frame independent): frames 0 / 17 / 31 of the B = 32 forward equal the same frames run
+        alone (B = 1) — the B = 1 path is the one held to the oracle above;
+      * decoder (frames COUPLED through the Look module: batch-wide max_len, first-B-rows / divide-by-B): the oracle's
+        decoder is run on the CPU at B = 32 on the product's own encoder outputs and every decoder output compared."""
+    from thinktwice_b200.synthetic import make_batch
+    cfg, oracle, model = full['cfg'], full['oracle'], full['model']
+    model.use_graph = False
+    B = 32
+    batch = make_batch(cfg, B, seed=21, num_points=40000)
+    pred = model.forward_inference(batch)
+    torch.cuda.synchronize()
+    e = model.eng
+    cam = model.last_cam_feat
+    keep32 = dict(cam_bev=cam['bev'].nchw().cpu().clone(), seg=cam['seg'].nchw().cpu().clone(),
+                  lidar=e.static_named('lidar.out.at').permute(0, 3, 1, 2).cpu().clone())
+    fpn = [f.nchw().cpu().clone() for f in cam['fpn_feats']]
+    flat = e.static_named('fu.py.flat').view(B, 256).cpu().clone()
+    bev32 = e.static_named('fu.m21.out').permute(0, 3, 1, 2).cpu().clone()
+    meas = e.static_named('meas').view(B, 128).cpu().clone()
+    lidar_hi = keep32['lidar']
+    out32 = {k: pred[k].float().cpu().clone() for k in ('pred_wp', 'mu_branches', 'sigma_branches', 'future_mu', 'future_sigma', 'pred_speed',
+                                                        'refine_flattned_BEV_feature', 'refine_BEV_feature')}
+    # ---- decoder at B = 32 against the oracle decoder on the same inputs
+    lidar2img = torch.stack([m[-1]['lidar2img'] for m in batch['img_metas']], 0).float()
+    ida = torch.stack([m[-1]['ida_mats'] for m in batch['img_metas']], 0).float()
+    with torch.no_grad():
+        ref = oracle.decoder(flat, bev32, meas, oracle, [lidar2img, ida, fpn, lidar_hi], False, None)
+    errs = {k: relerr(out32[k], ref[k]) for k in out32}
+    print({k: f'{v:.1e}' for k, v in errs.items()})
+    assert all(v <= TOL for v in errs.values()), errs
+    # ---- encoder: frame j of the batch == frame j alone
+    for j in (0, 17, 31):
+        one = {k: (v[j:j + 1] if torch.is_tensor(v) else v[j:j + 1]) for k, v in batch.items()}
+        model.forward_inference(one)
+        torch.cuda.synchronize()
+        c1 = model.last_cam_feat
+        assert relerr(c1['bev'].nchw(), keep32['cam_bev'][j:j + 1]) < 5e-4, j
+        assert relerr(c1['seg'].nchw(), keep32['seg'][j * 4:(j + 1) * 4]) < 5e-4, j
+        assert relerr(e.static_named('lidar.out.at').permute(0, 3, 1, 2), keep32['lidar'][j:j + 1]) < 5e-4, j

@@ -93,6 +93,7 @@ class Engine:
         self.device = torch.device(device)
         self.impl = impl
         self.bufs = {}
+        self.last_buf = {}
         self.cur = {}                 # name -> the buffer the latest upload(name, ...) went to (shape-keyed arena: see static())
         self.conv_ws = {}             # per lane: grow-only conv workspace (split-K partial sums of the SIMT kernel)
         self._ws_retired = []         # outgrown workspaces stay alive: CUDA graphs captured earlier still point at them
@@ -126,7 +127,12 @@ class Engine:
         if t is None:
             t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
             self.bufs[key] = t
+        self.last_buf[name] = t
         return t
+
+    def static_named(self, name):
+        """the buffer most recently requested under `name` (tests / debugging: a name can exist in several shapes)."""
+        return self.last_buf[name]
 
     def upload(self, name, t):
         """copy a host (or device) tensor into the persistent device buffer `name` (static address: graph-safe)."""
