@@ -94,7 +94,7 @@ int tt_lift_splat(const tt_lift_splat_desc* d, const float* depth_logits, const 
  * [N][yH][yW][y_ld] buffer (a k2s2 transposed conv is four such calls).
  * If m_count != NULL only the first *m_count rows (a device int) are computed.
  * `impl`: 0/1 = SIMT fp32 FFMA (exact), 2 = tcgen05 single-pass TF32 (operands rounded to nearest TF32),
- *         3 = tcgen05 3xTF32 (hi*hi + hi*lo + lo*hi, fp32-class).  impl 2/3 need stride 1 or 2, groups 1, channels,
+ *         3 = tcgen05 3xTF32 (hi*hi + hi*lo + lo*hi, fp32-class); 4 = scaled-split fp16 through tt_conv2d_f16s.  impl 2/3 need stride 1 or 2, groups 1, channels,
  *         x_ld, x_coff % 4 == 0 and 16-byte aligned x / w / y (TMA reads the activations in place and splits them in
  *         shared memory; no workspace); else TT_ERR_UNSUPPORTED.
  *         For impl 0/1 the workspace is optional: when given (size from tt_conv2d_workspace_bytes) small-M / large-K
@@ -121,6 +121,28 @@ typedef struct {
 size_t tt_conv2d_workspace_bytes(const tt_conv_desc* d);
 int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float* bias, const float* res,
               const float* res2, const int* gather, const int* m_count, float* y, void* workspace, tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2b) the same contraction on SCALED-SPLIT FP16 operands (impl 4, csrc/gemm_conv_f16s.cu) — the default tensor-core
+ * engine.  Replaces the same reference calls as (2): every torch.nn.Conv2d / ConvTranspose2d / Linear on the path
+ * (lss.py, encoder_decoder_framework.py:81-138, thinktwice_decoder.py) and spconv's convolutions (lidarnet.py:42-52).
+ * A "split" tensor is two __half planes over the SAME [N][H][W][ld] element grid as its fp32 twin:
+ *   hi = RN_f16(x),  lo' = RN_f16((x - hi) * 2048)   =>   x = hi + lo' / 2048 to 2^-22 relative (|x| < 65504).
+ * `x_split` / `y_split` point at the hi plane (already advanced to the tensor's channel offset); the lo' plane lies
+ * `*_plane` halves further.  Split activations are written by the producing kernel's epilogue (`y_split` here), so a
+ * consumer's TMA loads are tensor-core ready; tt_split_f16 converts fp32 rows produced by other kernels.
+ *   w_split: [2][Cout][taps][Cin8] halves, Cin8 = Cin rounded up to 8 (zero padded), plane 0 = hi, plane 1 = lo'.
+ *   products: hi*hi + (hi*lo' + lo'*hi) / 2048, fp32 accumulation drained into registers every 128 K elements.
+ *   y (fp32) and y_split are both optional outputs (at least one); res / res2 / bias are fp32 as in tt_conv2d.
+ * Needs groups 1, stride 1|2, x_ld % 8 == 0 (halves), y_ld % 4 == 0, 16-byte aligned pointers, else TT_ERR_UNSUPPORTED.
+ */
+int tt_conv2d_f16s(const tt_conv_desc* d, const void* x_split, long long x_plane, const void* w_split, const float* bias,
+                   const float* res, const float* res2, float* y, void* y_split, long long y_plane, tt_stream_t stream);
+/* fp32 rows [rows][x_ld] (first `cols` columns) -> split planes [2][rows][y_ld]; only the first *row_count rows when given */
+int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plane, long long y_ld, long long rows, int cols,
+                 const int* row_count, tt_stream_t stream);
+/* epilogue threads that had to clamp a value to +-65504 since the last reset (host int; synchronises `stream`) */
+int tt_f16s_saturation_count(unsigned int* out_host, int reset, tt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (3) memory-bound helpers (torch elementwise / pooling / interpolation ops)
@@ -219,6 +241,11 @@ typedef struct {
 int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_in, const float* w, const float* bias,
                    const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,
                    const int* out_count, float* feats_out, tt_stream_t stream);
+/* tt_sparse_conv on scaled-split fp16 operands (see 2b): feats_in_split [2][cap_in][in_ld] halves; writes the fp32 rows
+ * and, when out_split != NULL, their split planes [2][cap_out][out_ld].  w_split = [2][Cout][kvol][Cin8]. */
+int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split, long long in_plane, const void* w_split,
+                        const float* bias, const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,
+                        const int* out_count, float* feats_out, void* out_split, long long out_plane, tt_stream_t stream);
 /* dense()[N][C][D][H][W].view(N, C*D, H, W) (lidarnet.py:53-56) written channels-last, channel = c*D + z,
  * with the framework's anti-transpose (framework:246) folded in when asked; `dense` must be zero-filled. */
 int tt_sparse_to_bev(const float* feats, const int* coords, const int* count, int cap, int C, int D, int H, int W,

@@ -65,6 +65,13 @@ def _act(v, act):
     raise NotImplementedError(f'act {act}')
 
 
+def _split_f16(v):
+    """fp32 -> (hi, lo') halves exactly as csrc/gemm_conv_f16s.cu split_h (saturating)."""
+    c = v.float().clamp(-65504.0, 65504.0)
+    hi = c.half()
+    return hi, ((c - hi.float()) * 2048.0).half()
+
+
 def _pix_view(p, N, H, W, ld, nstride=0, hstride=0, C=None):
     """(N, H, W, C) strided view of a channels-last buffer starting at pointer p."""
     hs = hstride or W * ld
@@ -95,14 +102,27 @@ class Emu:
         raise NotImplementedError(f'emu_lib: {name}')
 
     # ------------------------------------------------------------------ conv / linear
-    def tt_conv2d(self, d, x, w, bias, res, res2, gather, m_count, y, ws, stream):
+    def tt_conv2d(self, d, x, w, bias, res, res2, gather, m_count, y, ws, stream, f16s=None):
         d = _desc(d)
         self.launches += 1
         assert not gather and not m_count
         taps = d.KH * d.KW
         cg, og = d.Cin // d.groups, d.Cout // d.groups
-        xin = _pix_view(x, d.N, d.H, d.W, d.x_ld, d.x_nstride, d.x_hstride, d.Cin).permute(0, 3, 1, 2).double()
-        if d.impl >= 2:                                                # [2][Cout][taps][Cin] hi / lo planes
+
+        def xview(C_):                                                 # (N, H, W, C_) fp64 view of the input
+            if f16s is None:
+                return _pix_view(x, d.N, d.H, d.W if C_ == d.Cin else d.x_hstride // d.x_ld, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
+            Wv = d.W if C_ == d.Cin else d.x_hstride // d.x_ld
+            hi = _pix_view(x, d.N, d.H, Wv, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
+            lo = _pix_view(Ptr(x.t, x.off + f16s['x_plane']), d.N, d.H, Wv, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
+            return hi + lo / 2048.0
+        xin = xview(d.Cin).permute(0, 3, 1, 2) if d.x_ld >= d.Cin else None
+        if f16s is not None:                                           # [2][Cout][taps][Cin8] scaled-split half planes
+            c8 = -(-d.Cin // 8) * 8
+            planes = w.flat()[:2 * d.Cout * taps * c8].view(2, d.Cout, taps, c8).double()
+            wt = (planes[0] + planes[1] / 2048.0)[..., :d.Cin].reshape(d.Cout, d.KH, d.KW, d.Cin).permute(0, 3, 1, 2)
+            assert d.groups == 1
+        elif d.impl >= 2:                                              # [2][Cout][taps][Cin] hi / lo planes
             planes = w.flat()[:2 * d.Cout * taps * d.Cin].view(2, d.Cout, taps, d.Cin).double()
             wt = (planes[0] + planes[1]).view(d.Cout, d.KH, d.KW, d.Cin).permute(0, 3, 1, 2)
             assert d.groups == 1
@@ -111,7 +131,7 @@ class Emu:
         if d.x_ld < d.Cin:                                             # row-packed input: channels run on into the next pixels
             assert d.KW == 1 and d.pad == 0 and d.groups == 1
             px = d.Cin // d.x_ld                                       # pixels per K slab
-            raw = _pix_view(x, d.N, d.H, d.x_hstride // d.x_ld, d.x_ld, d.x_nstride, d.x_hstride, d.x_ld).permute(0, 3, 1, 2).double()
+            raw = xview(d.x_ld).permute(0, 3, 1, 2)
             wt2 = wt.reshape(d.Cout, px, d.x_ld, d.KH).permute(0, 2, 3, 1)                  # (Cout, c, kh, kw)
             out = F.conv2d(raw, wt2, stride=d.stride)[..., :d.OH, :d.OW]
         else:
@@ -134,8 +154,34 @@ class Emu:
         if res2:
             out = out + _pix_view(res2, d.N, d.OH, d.OW, d.res2_ld, C=d.Cout + d.res2_coff)[..., d.res2_coff:].double()
         out = _act(out, d.act).float()
-        yv = _pix_view(y, d.N, d.yH, d.yW, d.y_ld, d.y_nstride, 0, d.Cout + d.y_coff)[..., d.y_coff:]
-        yv[:, d.oy_add::d.oy_mul, d.ox_add::d.ox_mul][:, :d.OH, :d.OW] = out
+        if y:
+            yv = _pix_view(y, d.N, d.yH, d.yW, d.y_ld, d.y_nstride, 0, d.Cout + d.y_coff)[..., d.y_coff:]
+            yv[:, d.oy_add::d.oy_mul, d.ox_add::d.ox_mul][:, :d.OH, :d.OW] = out
+        if f16s is not None and f16s['y_split']:
+            hi, lo = _split_f16(out)
+            for plane, val in ((0, hi), (f16s['y_plane'], lo)):
+                pv = Ptr(f16s['y_split'].t, f16s['y_split'].off + plane)
+                yv = _pix_view(pv, d.N, d.yH, d.yW, d.y_ld, d.y_nstride, 0, d.Cout + d.y_coff)[..., d.y_coff:]
+                yv[:, d.oy_add::d.oy_mul, d.ox_add::d.ox_mul][:, :d.OH, :d.OW] = val
+        return 0
+
+    def tt_conv2d_f16s(self, d, x_split, x_plane, w_split, bias, res, res2, y, y_split, y_plane, stream):
+        """include/tt_b200.h (2b): operands are read from the split planes (x = hi + lo' / 2048), outputs written as fp32 and / or split."""
+        assert x_split.t.dtype == torch.float16 and w_split.t.dtype == torch.float16
+        return self.tt_conv2d(d, x_split, w_split, bias, res, res2, NULL, NULL, y, NULL, stream,
+                              f16s=dict(x_plane=_v(x_plane), y_split=y_split, y_plane=_v(y_plane)))
+
+    def tt_split_f16(self, x, x_ld, y_split, y_plane, y_ld, rows, cols, row_count, stream):
+        self.launches += 1
+        x_ld, y_plane, y_ld, rows = _v(x_ld), _v(y_plane), _v(y_ld), _v(rows)
+        n = min(rows, int(row_count.flat()[0])) if row_count else rows
+        src = torch.as_strided(x.flat(), (n, cols), (x_ld, 1))
+        hi, lo = _split_f16(src)
+        torch.as_strided(y_split.flat(), (n, cols), (y_ld, 1)).copy_(hi)
+        torch.as_strided(Ptr(y_split.t, y_split.off + y_plane).flat(), (n, cols), (y_ld, 1)).copy_(lo)
+        return 0
+
+    def tt_f16s_saturation_count(self, out_host, reset, stream):
         return 0
 
     # ------------------------------------------------------------------ LiDAR: voxelise, rulebooks, sparse conv, densify
@@ -244,6 +290,35 @@ class Emu:
         if res:
             out += res.flat().view(-1, d.res_ld)[:n_out, :d.Cout].double()
         feats_out.flat().view(-1, d.out_ld)[:n_out, :d.Cout] = _act(out, d.act).float()
+        return 0
+
+    def tt_sparse_conv_f16s(self, d, feats_in_split, in_plane, w_split, bias, res, pairs_in, pairs_out, pair_count, out_count, feats_out,
+                            out_split, out_plane, stream):
+        d = _desc(d)
+        self.launches += 3
+        in_plane, out_plane = _v(in_plane), _v(out_plane)
+        n_out = int(out_count.flat()[0])
+        fi = (feats_in_split.flat().view(-1, d.in_ld)[:in_plane // d.in_ld, :d.Cin].double() +
+              Ptr(feats_in_split.t, feats_in_split.off + in_plane).flat().view(-1, d.in_ld)[:in_plane // d.in_ld, :d.Cin].double() / 2048.0)
+        c8 = -(-d.Cin // 8) * 8
+        planes = w_split.flat()[:2 * d.Cout * d.kvol * c8].view(2, d.Cout, d.kvol, c8).double()
+        wt = (planes[0] + planes[1] / 2048.0)[..., :d.Cin].permute(1, 2, 0)   # (kvol, Cin, Cout)
+        out = torch.zeros(n_out, d.Cout, dtype=torch.float64)
+        if bias:
+            out += bias.flat()[:d.Cout].double()
+        pin, pout = pairs_in.flat().view(d.kvol, -1), pairs_out.flat().view(d.kvol, -1)
+        for t in range(d.kvol):
+            m = int(pair_count.flat()[t])
+            if m:
+                out.index_add_(0, pout[t, :m].long(), fi[pin[t, :m].long()] @ wt[t])
+        if res:
+            out += res.flat().view(-1, d.res_ld)[:n_out, :d.Cout].double()
+        o = _act(out, d.act).float()
+        feats_out.flat().view(-1, d.out_ld)[:n_out, :d.Cout] = o
+        if out_split:
+            hi, lo = _split_f16(o)
+            out_split.flat().view(-1, d.out_ld)[:n_out, :d.Cout] = hi
+            Ptr(out_split.t, out_split.off + out_plane).flat().view(-1, d.out_ld)[:n_out, :d.Cout] = lo
         return 0
 
     def tt_sparse_to_bev(self, feats, coords, count, cap, Cc, D, H, W, anti, dense, stream):

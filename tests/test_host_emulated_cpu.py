@@ -30,7 +30,7 @@ def _pair(cfg_path, B, points, seed, impl, sweeps=None):
     return o, m, batch
 
 
-@pytest.mark.parametrize('impl,B,seed,sweeps', [(1, 1, 0, None), (3, 1, 0, None), (3, 2, 1, None), (3, 1, 2, 2)])
+@pytest.mark.parametrize('impl,B,seed,sweeps', [(1, 1, 0, None), (3, 1, 0, None), (3, 2, 1, None), (3, 1, 2, 2), (4, 1, 0, None), (4, 2, 1, None), (4, 1, 2, 2)])
 def test_plumbing_forward_through_the_emulated_abi_matches_the_oracle(emulated, impl, B, seed, sweeps):
     """impl 1: SIMT weight layouts; impl 3: the tensor-core layouts (hi / lo planes, row-packed stem, padded thin convs, per-group
     DCN GEMMs, sparse-conv planes); B = 2 exercises the batch-coupled Look semantics on the product side; sweeps = 2 the history

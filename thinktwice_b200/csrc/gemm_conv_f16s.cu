@@ -1,0 +1,784 @@
+// tcgen05 implicit-GEMM convolution on SCALED-SPLIT FP16 operands ("f16s") for sm_100a — the round-2 successor of the
+// 3xTF32 kernel in gemm_conv_tc.cu (same tiling, same epilogue contract, same fp32-class accuracy, half the operand bytes
+// and twice the tensor-core rate).
+//
+// Operand format.  An fp32 value x is carried as two halves:  hi = RN_f16(x),  lo = RN_f16((x - hi) * 2^11).
+//   x - hi is exact in fp32 and |x - hi| <= 2^-11 |x|, so lo is O(|x|) again (no fp16 underflow of the correction) and
+//   x = hi + lo * 2^-11 to 2^-22 relative (fp16 has the same 11 significant bits as TF32): the same representation error as
+//   the TF32 hi / lo split, at 4 bytes per element instead of 8.  Activations live in HBM in this form next to (or instead
+//   of) their fp32 copy: a "split" tensor is two half planes [2][N][H][W][ld] written by the PRODUCING kernel's epilogue, so
+//   the consumer's TMA loads deliver tensor-core-ready operands — no split warps, no shared-memory rewrite (the 3xTF32
+//   kernel's measured roof was shared-memory traffic: 176 KB per 32-float K slab, profiles/r1_tc_full_summary.md).
+//   Range: |x| must stay below 65504 (hi saturates; counted in g_f16s_saturated, read with tt_f16s_saturation_count).
+// Products.  Per K step (16 halves) two instructions, exactly the 3-product scheme of the TF32 kernel:
+//   main | corr  +=  A_hi x [B_hi ; B_lo']      one N = 2 BN tcgen05.mma.kind::f16 (B_lo' follows B_hi in shared memory)
+//   corr         +=  A_lo' x B_hi
+//   result = main + 2^-11 corr  (the dropped lo x lo term is 2^-22 relative).  kind::f16 K = 16 per instruction, so a K of
+//   128 costs the 8 truncating accumulations that 64 cost in TF32: chunks (TMEM ping-pong drains into fp32 registers, see
+//   gemm_conv_tc.cu) are twice as long at the same accumulated rounding error.
+// Everything else follows gemm_conv_tc.cu: TMA box loads per tap (zero fill = padding, element strides = stride 2), CTA pairs
+// with multicast weight halves, persistent tiles, 8 epilogue warps with coalesced stores, split-K and GATHER (sparse conv).
+// Warp roles: warp 0 = TMA / gather producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+extern long long g_tt_launches;
+extern int g_tt_debug;
+
+__device__ unsigned int g_f16s_saturated = 0;     // number of values an epilogue had to clamp to the fp16 range
+
+namespace {
+
+constexpr int BM = 128;           // UMMA M
+constexpr int KE = 64;            // K elements per stage (one 128-byte swizzle row of halves)
+constexpr int NTHREADS = 320;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+constexpr int MAX_KVOL = 32;
+constexpr float H_MAX = 65504.f;
+
+// kind::f16 instruction descriptor: c_format F32 (1) @4, a/b_format F16 (0) @7/@10, K-major, N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+TT_DEVICE void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+TT_DEVICE void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+TT_DEVICE void tma_load_4d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+
+// x -> (hi, lo') with saturation to the fp16 range; returns true when x had to be clamped
+TT_DEVICE bool split_h(float x, __half& hi, __half& lo) {
+  const float c = fminf(fmaxf(x, -H_MAX), H_MAX);
+  hi = __float2half_rn(c);
+  lo = __float2half_rn((c - __half2float(hi)) * LO_SCALE);
+  return c != x;
+}
+TT_DEVICE void split4(const float4& o, uint2& hi, uint2& lo, bool& sat) {
+  __half h[4], l[4];
+  sat |= split_h(o.x, h[0], l[0]);
+  sat |= split_h(o.y, h[1], l[1]);
+  sat |= split_h(o.z, h[2], l[2]);
+  sat |= split_h(o.w, h[3], l[3]);
+  hi.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+  hi.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+  lo.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+  lo.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+}
+
+struct HArgs {
+  tt_conv_desc d;
+  const float* bias;
+  const float* res;
+  const float* res2;
+  float* y;              // fp32 output (may be NULL when only the split planes are wanted)
+  __half* ys;            // split output: hi plane at the same element offsets as y; lo' plane ys_plane halves further (or NULL)
+  long long ys_plane;
+  int TH, TW;            // tile rectangle (TH * TW <= 128); flat mode: TH = 1, TW = 128 over N*H*W pixels
+  int tiles_w, tiles_h;
+  int flat;
+  int n_slabs;           // ceil(Cin / 64)
+  int chunk;             // stages accumulated inside TMEM before the epilogue folds them into fp32 registers
+  int total_pix;
+  int dbg;
+  int m_tiles, n_tiles;
+  // GATHER (tap-major sparse convolution)
+  const __half* gx;      // split feature rows: hi plane [.][gx_ld], lo' plane gx_plane halves further
+  long long gx_plane;
+  int gx_ld;
+  const int* pairs_in;
+  const int* pairs_out;
+  const int* pair_count;
+  int kvol, pair_cap;
+  int splits, k_per;     // split-K: K stages per split
+};
+
+template <int BN, int STAGES, bool GATHER>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_BYTES = BM * KE * 2;                    // 16 KB per plane
+  constexpr int B_BYTES = BN * KE * 2;                    // per plane
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int ACC_COLS = 2 * BN;                        // main | corr
+  constexpr int TMEM_COLS = 2 * ACC_COLS;                 // ping-pong
+  constexpr int SLAB = 16;
+  constexpr int PITCH = SLAB + 4;
+  constexpr int HN = BN / 2;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* tile_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);              // [8 warps][32 rows][PITCH]
+  long long* row_y = reinterpret_cast<long long*>(tile_all + 8 * 32 * PITCH);
+  long long* row_r1 = row_y + BM;
+  long long* row_r2 = row_r1 + BM;
+  int* row_flag = reinterpret_cast<int*>(row_r2 + BM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(row_flag + BM);
+  uint64_t* full = bars;                                  // [STAGES]  producer -> MMA (operands landed)
+  uint64_t* empty = bars + STAGES;                        // [STAGES]  MMA -> producer
+  uint64_t* acc_full = bars + 2 * STAGES;                 // [2]       MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;            // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  int* sp_first = reinterpret_cast<int*>(tmem_slot + 2);
+  int* sp_cnt = sp_first + MAX_KVOL + 1;
+
+  const tt_conv_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = d.KH * d.KW;
+  const int k_iters = taps * p.n_slabs;
+  const uint32_t rank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], 2); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (GATHER && threadIdx.x == 64) {
+    int acc = 0;
+    for (int t = 0; t < p.kvol; ++t) {
+      const int c = min(p.pair_count[t], p.pair_cap);
+      sp_cnt[t] = c;
+      sp_first[t] = acc;
+      acc += ((c + BM - 1) / BM + 1) / 2;
+    }
+    sp_first[p.kvol] = acc;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_pairs = (GATHER ? sp_first[p.kvol] : (p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+  auto decode = [&](int pt, int& nt, int& mt, int& tap, int& count, int& kb, int& ke) {
+    const int ks = pt % p.splits;
+    pt /= p.splits;
+    kb = ks * p.k_per;
+    ke = min(k_iters, kb + p.k_per);
+    nt = pt % p.n_tiles;
+    const int pm = pt / p.n_tiles;
+    tap = 0; count = 0;
+    if (GATHER) {
+      while (sp_first[tap + 1] <= pm) ++tap;
+      mt = 2 * (pm - sp_first[tap]) + (int)rank;
+      count = sp_cnt[tap];
+    } else {
+      mt = 2 * pm + (int)rank;
+    }
+  };
+
+  if (warp == 0 && GATHER) {
+    // ===================================================================== gather producer (whole warp) + weight TMA
+    const uint32_t txb = 2 * B_BYTES;
+    int ig = 0;
+    for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+      int nt, mt, tap, count, kb, ke;
+      decode(pt, nt, mt, tap, count, kb, ke);
+      const int n0 = nt * BN;
+      const int* pin = p.pairs_in + (long long)tap * p.pair_cap;
+      int rows[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = mt * BM + lane + 32 * i;
+        rows[i] = m < count ? __ldg(pin + m) : -1;
+      }
+      for (int it = kb; it < ke; ++it, ++ig) {
+        const int s = ig % STAGES;
+        mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        if (lane == 0) {
+          mbar_expect_tx(&full[s], txb);
+          tma_load_4d_mc(st + 2 * A_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], it * KE, tap, n0 + (int)rank * (BN / 2), 0, 3);
+          tma_load_4d_mc(st + 2 * A_BYTES + B_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], it * KE, tap, n0 + (int)rank * (BN / 2), 1, 3);
+        }
+        const int c0 = it * KE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = lane + 32 * i;
+          const __half* src = p.gx + (long long)max(rows[i], 0) * p.gx_ld + c0;
+          const uint32_t dst = smem_u32(st) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {                       // 16-byte chunk j (8 halves) of row r lives at chunk j ^ (r & 7)
+            const bool ok = rows[i] >= 0 && c0 + j * 8 < d.Cin;
+            const uint32_t o = (uint32_t)((j ^ (r & 7)) << 4);
+            cp_async16(dst + o, ok ? (const void*)(src + j * 8) : (const void*)p.gx, ok ? 16 : 0);
+            cp_async16(dst + A_BYTES + o, ok ? (const void*)(src + p.gx_plane + j * 8) : (const void*)p.gx, ok ? 16 : 0);
+          }
+        }
+        cp_async_arrive_noinc(&full[s]);
+      }
+    }
+  } else if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KE * 2;   // bytes one activation box (one plane) delivers
+      const uint32_t tx = ((p.dbg & 2) ? 0u : 2 * a_box) + 2 * B_BYTES;
+      int ig = 0;
+      for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+        int nt, mt, tap0, count, kb, ke;
+        decode(pt, nt, mt, tap0, count, kb, ke);
+        const int n0 = nt * BN;
+        int cw0, ch0, cn;
+        if (p.flat) { cw0 = mt * BM; ch0 = 0; cn = 0; }
+        else {
+          const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h;
+          cn = mt / (p.tiles_w * p.tiles_h);
+          cw0 = tw * p.TW * d.stride - d.pad; ch0 = th * p.TH * d.stride - d.pad;
+        }
+        for (int it = kb; it < ke; ++it, ++ig) {
+          const int s = ig % STAGES;
+          mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          const int tap = it / p.n_slabs, slab = it - tap * p.n_slabs;
+          const int kh = tap / d.KW, kw = tap - kh * d.KW;
+          mbar_expect_tx(&full[s], tx);
+          if (!(p.dbg & 2)) {
+            if (p.flat) {
+              tma_load_3d(st, &map_a, &full[s], slab * KE, cw0, 0);
+              tma_load_3d(st + A_BYTES, &map_a, &full[s], slab * KE, cw0, 1);
+            } else {
+              const int cw = cw0 + kw * d.dil, ch = ch0 + kh * d.dil;
+              tma_load_5d(st, &map_a, &full[s], slab * KE, cw, ch, cn, 0);
+              tma_load_5d(st + A_BYTES, &map_a, &full[s], slab * KE, cw, ch, cn, 1);
+            }
+          }
+          tma_load_4d_mc(st + 2 * A_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], slab * KE, tap, n0 + (int)rank * (BN / 2), 0, 3);
+          tma_load_4d_mc(st + 2 * A_BYTES + B_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], slab * KE, tap, n0 + (int)rank * (BN / 2), 1, 3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      constexpr uint32_t idesc2 = make_idesc_f16(BM, 2 * BN);
+      int ig = 0, cg = 0;
+      for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+        int nt, mt, tap0, count, kb, ke;
+        decode(pt, nt, mt, tap0, count, kb, ke);
+        int it = kb;
+        const int nch = (ke - kb + p.chunk - 1) / p.chunk;
+        for (int c = 0; c < nch; ++c, ++cg) {
+          const int b = cg & 1;
+          mbar_wait(&acc_empty[b], ((cg >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t t_main = tmem_base + (uint32_t)(b * ACC_COLS), t_corr = t_main + BN;
+          const int it_end = min(it + p.chunk, ke);
+          bool first = true;
+          for (; it < it_end; ++it, ++ig) {
+            const int s = ig % STAGES;
+            mbar_wait(&full[s], (ig / STAGES) & 1);
+            tcgen05_fence_after();
+            const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < KE / 16; ++kk) {           // UMMA K = 16 halves = 32 bytes inside the 128-byte swizzle row
+              if (p.dbg & 4) break;
+              const uint32_t off = kk * 32;
+              const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+              umma_f16(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc2, acc);   // hi*hi | hi*lo'
+              umma_f16(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);      // lo'*hi
+            }
+            first = false;
+            tcgen05_commit_mc(&empty[s], 3);
+          }
+          tcgen05_commit(&acc_full[b]);
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+    const int HWo = d.OH * d.OW;
+    float* tile = tile_all + (warp - 2) * 32 * PITCH;
+    bool sat = false;
+    int cg = 0;
+    for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+      int nt, mt, tap, count, kb, ke;
+      decode(pt, nt, mt, tap, count, kb, ke);
+      const int nch = (ke - kb + p.chunk - 1) / p.chunk;
+      const bool real_tile = GATHER ? mt * BM < count : mt < p.m_tiles;
+      const int n0 = nt * BN + half * HN;
+      if (GATHER) {
+        const int m = mt * BM + r;
+        const bool valid = m < count;
+        if (half == 0) {
+          const int orow = valid ? __ldg(p.pairs_out + (long long)tap * p.pair_cap + m) : 0;
+          row_y[r] = (long long)orow * d.y_ld + d.y_coff;
+          row_r1[r] = 0;
+          row_r2[r] = 0;
+          row_flag[r] = valid ? 1 : 0;
+        }
+      } else {
+        bool valid;
+        int nimg, oh, ow;
+        long long rrow;
+        if (p.flat) {
+          const long long pix = (long long)mt * BM + r;
+          valid = real_tile && pix < p.total_pix;
+          nimg = (int)(pix / HWo);
+          const int rem = (int)(pix - (long long)nimg * HWo);
+          oh = rem / d.OW; ow = rem - oh * d.OW;
+          rrow = pix;
+        } else {
+          const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h;
+          nimg = mt / (p.tiles_w * p.tiles_h);
+          const int rh = r / p.TW, rw = r - rh * p.TW;
+          oh = th * p.TH + rh; ow = tw * p.TW + rw;
+          valid = real_tile && (r < p.TH * p.TW) && oh < d.OH && ow < d.OW;
+          rrow = ((long long)nimg * d.OH + oh) * d.OW + ow;
+        }
+        const long long r1 = (d.res_mode == TT_RES_UP2_NEAREST
+                                  ? ((long long)nimg * d.res_H + (oh * d.res_H) / d.OH) * d.res_W + (ow * d.res_W) / d.OW
+                                  : rrow) * d.res_ld + d.res_coff;
+        const long long r2 = rrow * d.res2_ld + d.res2_coff;
+        if (half == 0) {
+          row_y[r] = nimg * yns + ((long long)(oh * d.oy_mul + d.oy_add) * d.yW + ow * d.ox_mul + d.ox_add) * d.y_ld + d.y_coff;
+          row_r1[r] = r1;
+          row_r2[r] = r2;
+          row_flag[r] = (valid ? 1 : 0) | (nimg << 1);
+        }
+        if (valid && n0 < d.Cout) {
+          if (p.res) {
+#pragma unroll
+            for (int j = 0; j < HN; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + r1 + n0 + j));
+          }
+          if (p.res2) {
+#pragma unroll
+            for (int j = 0; j < HN; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res2 + r2 + n0 + j));
+          }
+        }
+      }
+      float sum[HN];
+#pragma unroll
+      for (int j = 0; j < HN; ++j) sum[j] = 0.f;
+      for (int c = 0; c < nch; ++c, ++cg) {
+        const int b = cg & 1;
+        mbar_wait(&acc_full[b], (cg >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * ACC_COLS + half * HN);
+#pragma unroll
+        for (int c0 = 0; c0 < HN; c0 += 32) {
+          uint32_t v[32], u[32];
+          tmem_ld32(t_main + c0, v);
+          tmem_ld32(t_main + BN + c0, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c0 + j] += fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j]));   // fp32 RN
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int sub = lane >> 2, cl = (lane & 3) * 4;
+#pragma unroll
+      for (int sl = 0; sl < HN / SLAB; ++sl) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < SLAB; j += 4)
+          *reinterpret_cast<float4*>(&tile[lane * PITCH + j]) =
+              make_float4(sum[sl * SLAB + j], sum[sl * SLAB + j + 1], sum[sl * SLAB + j + 2], sum[sl * SLAB + j + 3]);
+        __syncwarp();
+        const int col = n0 + sl * SLAB + cl;
+        if (col < d.Cout && !(p.dbg & 1)) {
+          float4 acc4[4], ra[4], rb[4];
+          int fl[4];
+          long long yo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int lr = i * 8 + sub, rr = q * 32 + lr;
+            fl[i] = row_flag[rr];
+            yo[i] = row_y[rr];
+            acc4[i] = *reinterpret_cast<const float4*>(&tile[lr * PITCH + cl]);
+            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[i] = ra[i];
+            if (fl[i] & 1) {
+              if (p.res) ra[i] = *reinterpret_cast<const float4*>(p.res + row_r1[rr] + col);
+              if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + row_r2[rr] + col);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!(fl[i] & 1)) continue;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout : 0) + col));
+            float4 o = make_float4(acc4[i].x + bv.x + ra[i].x + rb[i].x, acc4[i].y + bv.y + ra[i].y + rb[i].y,
+                                   acc4[i].z + bv.z + ra[i].z + rb[i].z, acc4[i].w + bv.w + ra[i].w + rb[i].w);
+            const long long eo = yo[i] + col;
+            if (GATHER || p.splits > 1) {                      // taps / K splits race on an output row: red.add (fp32 only)
+              tt_red_add_v4(p.y + eo, o.x, o.y, o.z, o.w);
+            } else {
+              o = make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
+              if (p.y) *reinterpret_cast<float4*>(p.y + eo) = o;
+              if (p.ys) {
+                uint2 hi, lo;
+                split4(o, hi, lo, sat);
+                *reinterpret_cast<uint2*>(p.ys + eo) = hi;
+                *reinterpret_cast<uint2*>(p.ys + p.ys_plane + eo) = lo;
+              }
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    if (sat) atomicAdd(&g_f16s_saturated, 1u);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// split-K / sparse companions.  init: y = bias + res + res2 before the tensor-core kernel red.adds its partial sums;
+// finish: y = act(y) and, when asked, the split planes of the finished rows.
+__global__ void f16s_splitk_init_kernel(const tt_conv_desc d, const float* __restrict__ bias, const float* __restrict__ res,
+                                        const float* __restrict__ res2, float* __restrict__ y) {
+  const int HWo = d.OH * d.OW, C4 = d.Cout / 4;
+  const long long total = (long long)d.N * HWo * C4;
+  const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long pix = i / C4;
+    const int n = (int)(pix / HWo);
+    float4 v = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) { const float4 t = *reinterpret_cast<const float4*>(res + pix * d.res_ld + d.res_coff + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    if (res2) { const float4 t = *reinterpret_cast<const float4*>(res2 + pix * d.res2_ld + d.res2_coff + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    *reinterpret_cast<float4*>(y + n * yns + (pix - (long long)n * HWo) * d.y_ld + d.y_coff + c) = v;
+  }
+}
+__global__ void f16s_splitk_finish_kernel(const tt_conv_desc d, float* __restrict__ y, __half* __restrict__ ys, long long ys_plane) {
+  const int HWo = d.OH * d.OW, C4 = d.Cout / 4;
+  const long long total = (long long)d.N * HWo * C4;
+  const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
+  bool sat = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long pix = i / C4;
+    const int n = (int)(pix / HWo);
+    const long long eo = n * yns + (pix - (long long)n * HWo) * d.y_ld + d.y_coff + c;
+    float4 v = *reinterpret_cast<const float4*>(y + eo);
+    v = make_float4(tt_act(v.x, d.act), tt_act(v.y, d.act), tt_act(v.z, d.act), tt_act(v.w, d.act));
+    if (d.act != TT_ACT_NONE) *reinterpret_cast<float4*>(y + eo) = v;
+    if (ys) {
+      uint2 hi, lo;
+      split4(v, hi, lo, sat);
+      *reinterpret_cast<uint2*>(ys + eo) = hi;
+      *reinterpret_cast<uint2*>(ys + ys_plane + eo) = lo;
+    }
+  }
+  if (sat) atomicAdd(&g_f16s_saturated, 1u);
+}
+
+// generic fp32 rows -> split planes (producers that are not convolutions: pooling, resampling, gating, staging of inputs)
+__global__ void split_rows_kernel(const float* __restrict__ x, long long x_ld, __half* __restrict__ ys, long long ys_plane,
+                                  long long ys_ld, long long rows, int cols4, const int* __restrict__ row_count) {
+  const long long total = (row_count ? min((long long)*row_count, rows) : rows) * cols4;
+  bool sat = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * x_ld + c);
+    uint2 hi, lo;
+    split4(v, hi, lo, sat);
+    *reinterpret_cast<uint2*>(ys + r * ys_ld + c) = hi;
+    *reinterpret_cast<uint2*>(ys + ys_plane + r * ys_ld + c) = lo;
+  }
+  if (sat) atomicAdd(&g_f16s_saturated, 1u);
+}
+
+// sparse rows: y = act(y + res) for the first *count rows, plus their split planes
+__global__ void f16s_sparse_finish_kernel(float* __restrict__ y, int y_ld, const float* __restrict__ res, int res_ld, int C,
+                                          const int* __restrict__ count, int cap, int act, __half* __restrict__ ys, long long ys_plane) {
+  const int C4 = C / 4;
+  const long long total = (long long)min(*count, cap) * C4;
+  bool sat = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(y + r * y_ld + c);
+    if (res) { const float4 t = *reinterpret_cast<const float4*>(res + r * res_ld + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    v = make_float4(tt_act(v.x, act), tt_act(v.y, act), tt_act(v.z, act), tt_act(v.w, act));
+    *reinterpret_cast<float4*>(y + r * y_ld + c) = v;
+    if (ys) {
+      uint2 hi, lo;
+      split4(v, hi, lo, sat);
+      *reinterpret_cast<uint2*>(ys + r * y_ld + c) = hi;
+      *reinterpret_cast<uint2*>(ys + ys_plane + r * y_ld + c) = lo;
+    }
+  }
+  if (sat) atomicAdd(&g_f16s_saturated, 1u);
+}
+__global__ void f16s_sparse_init_kernel(float* __restrict__ y, int y_ld, const float* __restrict__ bias, int C,
+                                        const int* __restrict__ count, int cap) {
+  const int C4 = C / 4;
+  const long long total = (long long)min(*count, cap) * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4;
+    const int c = (int)(i - r * C4) * 4;
+    *reinterpret_cast<float4*>(y + r * y_ld + c) = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+int num_sms_cached() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+  return n;
+}
+constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;
+
+template <int BN, int STAGES, bool GATHER>
+cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
+  constexpr int smem = STAGES * (2 * BM * KE * 2 + 2 * BN * KE * 2) + 1024 + EPI_BYTES;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+  cfg.dynamicSmemBytes = smem;
+  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER>, ma, mb, a);
+}
+
+bool encode_weights(CUtensorMap* mb, const void* w_split, int Cin, int taps, int Cout, int BN) {
+  const int cin_pad = (Cin + 7) & ~7;
+  cuuint64_t dims[4] = {(cuuint64_t)cin_pad, (cuuint64_t)taps, (cuuint64_t)Cout, 2};
+  cuuint64_t str[3] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)taps * cin_pad * 2, (cuuint64_t)Cout * taps * cin_pad * 2};
+  cuuint32_t box[4] = {KE, 1, (cuuint32_t)(BN / 2), 1};          // each CTA of a pair loads (and multicasts) half of a plane's slab
+  return encode_map(mb, w_split, 4, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* number of epilogue threads that clamped a value to +-65504 since the last call (synchronises `stream`) */
+int tt_f16s_saturation_count(unsigned int* out_host, int reset, tt_stream_t stream) {
+  TT_REQUIRE(out_host, "tt_f16s_saturation_count", "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemcpyFromSymbolAsync(out_host, g_f16s_saturated, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {
+    tt_set_error("tt_f16s_saturation_count: %s", cudaGetErrorString(cudaGetLastError()));
+    return TT_ERR_CUDA;
+  }
+  if (reset) {
+    const unsigned int z = 0;
+    if (cudaMemcpyToSymbolAsync(g_f16s_saturated, &z, sizeof(z), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return TT_ERR_CUDA;
+    cudaStreamSynchronize(st);
+  }
+  return TT_OK;
+}
+
+int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plane, long long y_ld, long long rows, int cols,
+                 const int* row_count, tt_stream_t stream) {
+  TT_REQUIRE(x && y_split && rows >= 0 && cols > 0, "tt_split_f16", "bad argument");
+  TT_REQUIRE(cols % 4 == 0 && x_ld % 4 == 0 && y_ld % 4 == 0 && y_plane % 4 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y_split) & 7) == 0),
+             "tt_split_f16", "needs 4-element alignment");
+  if (rows == 0) return TT_OK;
+  const long long total = rows * (cols / 4);
+  const int nb = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  split_rows_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, x_ld, static_cast<__half*>(y_split), y_plane, y_ld, rows, cols / 4, row_count);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_split_f16");
+  return TT_OK;
+}
+
+int tt_conv2d_f16s(const tt_conv_desc* d, const void* x_split, long long x_plane, const void* w_split, const float* bias,
+                   const float* res, const float* res2, float* y, void* y_split, long long y_plane, tt_stream_t stream) {
+  TT_REQUIRE(d && x_split && w_split && (y || y_split), "tt_conv2d_f16s", "null argument");
+  TT_REQUIRE(d->res_mode == TT_RES_NONE || res != nullptr, "tt_conv2d_f16s", "res_mode set without a residual");
+  const long long xhs = d->x_hstride ? d->x_hstride : (long long)d->W * d->x_ld;
+  const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * xhs;
+  const bool ok = d->groups == 1 && (d->stride == 1 || d->stride == 2) && d->Cout % 4 == 0 && d->x_ld % 8 == 0 && xhs % 8 == 0 &&
+                  xns % 8 == 0 && x_plane % 8 == 0 && d->y_ld % 4 == 0 && d->y_coff % 4 == 0 && d->y_nstride % 4 == 0 && y_plane % 4 == 0 &&
+                  (d->res_mode == TT_RES_NONE || d->res_ld % 4 == 0) && d->res2_ld % 4 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(x_split) | reinterpret_cast<uintptr_t>(w_split) | reinterpret_cast<uintptr_t>(y) |
+                    reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(res2) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(y_split) & 7) == 0 &&
+                  d->OH == (d->H + 2 * d->pad - d->dil * (d->KH - 1) - 1) / d->stride + 1 &&
+                  d->OW == (d->W + 2 * d->pad - d->dil * (d->KW - 1) - 1) / d->stride + 1;
+  if (!ok) {
+    tt_set_error("tt_conv2d_f16s: unsupported shape / alignment (groups 1, stride 1|2, x_ld %% 8, y_ld %% 4, 16-byte aligned pointers)");
+    return TT_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = d->KH * d->KW;
+  const long long npix_in = (long long)d->N * d->H * d->W;
+  HArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = *d;
+  a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
+  a.ys = static_cast<__half*>(y_split); a.ys_plane = y_plane;
+  a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;   // 2 stages = K 128 = 8 truncating accumulations per chunk
+  a.n_slabs = (d->Cin + KE - 1) / KE;
+  a.total_pix = d->N * d->OH * d->OW;
+  a.flat = (taps == 1 && d->pad == 0 && d->stride == 1 && xhs == (long long)d->W * d->x_ld && xns == (long long)d->H * xhs) ? 1 : 0;
+  CUtensorMap ma, mb;
+  int grid_x;
+  if (a.flat) {
+    a.TH = 1; a.TW = BM; a.tiles_w = a.tiles_h = 1;
+    cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)npix_in, 2};
+    cuuint64_t str[2] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)x_plane * 2};
+    cuuint32_t box[3] = {KE, BM, 1};
+    if (!encode_map(&ma, x_split, 3, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16)) return TT_ERR_CUDA;
+    grid_x = tt_cdiv(npix_in, BM);
+  } else {
+    int best_th = 1, best_tw = 1;
+    double best = -1;
+    for (int tw = 1; tw <= 128 && tw * d->stride <= 256; ++tw) {
+      const int th = 128 / tw;
+      if (th < 1) break;
+      const double cover = (double)d->OW * d->OH / ((double)tt_cdiv(d->OW, tw) * tw * tt_cdiv(d->OH, th) * th);
+      const double eff = cover * (tw * th) / 128.0;
+      if (eff > best + 1e-9) { best = eff; best_th = th; best_tw = tw; }
+    }
+    a.TH = best_th; a.TW = best_tw;
+    a.tiles_w = tt_cdiv(d->OW, a.TW); a.tiles_h = tt_cdiv(d->OH, a.TH);
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N, 2};
+    cuuint64_t str[4] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)xhs * 2, (cuuint64_t)xns * 2, (cuuint64_t)x_plane * 2};
+    cuuint32_t box[5] = {KE, (cuuint32_t)(a.TW * d->stride), (cuuint32_t)(a.TH * d->stride), 1, 1};
+    if (!encode_map(&ma, x_split, 5, dims, str, box, d->stride, CU_TENSOR_MAP_DATA_TYPE_FLOAT16)) return TT_ERR_CUDA;
+    grid_x = a.tiles_w * a.tiles_h * d->N;
+  }
+  const int BN = d->Cout > 64 ? 128 : 64;
+  if (!encode_weights(&mb, w_split, d->Cin, taps, d->Cout, BN)) return TT_ERR_CUDA;
+  a.dbg = g_tt_debug & 0xFF;
+  a.m_tiles = grid_x;
+  a.n_tiles = tt_cdiv(d->Cout, BN);
+  const int num_sms = num_sms_cached();
+  const int k_iters = taps * a.n_slabs;
+  a.splits = 1;
+  a.k_per = k_iters;
+  {
+    const long long tile_pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles;
+    const bool plain = y != nullptr && d->oy_mul == 1 && d->ox_mul == 1 && d->oy_add == 0 && d->ox_add == 0 && d->yH == d->OH && d->yW == d->OW &&
+                       d->res_mode != TT_RES_UP2_NEAREST && d->bias_n_mod == 0 && !(g_tt_debug & 128);
+    if (plain && tile_pairs * 2 <= num_sms / 2 && k_iters >= 8) {
+      int sp = (int)((num_sms / 2 + tile_pairs - 1) / tile_pairs);
+      if (sp > k_iters / 4) sp = k_iters / 4;
+      if (sp > 32) sp = 32;
+      if (sp >= 2) {
+        a.k_per = tt_cdiv(k_iters, sp);
+        a.splits = tt_cdiv(k_iters, a.k_per);
+      }
+    }
+  }
+  const long long total4 = (long long)d->N * d->OH * d->OW * (d->Cout / 4);
+  const int nb_ew = (int)((total4 + 255) / 256 > 1184 ? 1184 : (total4 + 255) / 256);
+  if (a.splits > 1) {
+    f16s_splitk_init_kernel<<<nb_ew, 256, 0, st>>>(*d, bias, d->res_mode != TT_RES_NONE ? res : nullptr, res2, y);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_conv2d_f16s(split-k init)");
+    a.bias = nullptr; a.res = nullptr; a.res2 = nullptr;
+    a.d.act = TT_ACT_NONE;
+    a.d.res_mode = TT_RES_NONE;
+  }
+  const long long pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles * a.splits;
+  const long long max_pairs = (num_sms - ((g_tt_debug >> 8) & 0xFF)) / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, false>(cfg, ma, mb, a) : launch_f16s<64, 4, false>(cfg, ma, mb, a);
+  if (lerr != cudaSuccess) { tt_set_error("tt_conv2d_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_conv2d_f16s");
+  if (a.splits > 1 && (d->act != TT_ACT_NONE || y_split)) {
+    f16s_splitk_finish_kernel<<<nb_ew, 256, 0, st>>>(*d, y, static_cast<__half*>(y_split), y_plane);
+    ++g_tt_launches;
+    TT_CHECK_LAUNCH("tt_conv2d_f16s(split-k finish)");
+  }
+  return TT_OK;
+}
+
+int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split, long long in_plane, const void* w_split,
+                        const float* bias, const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,
+                        const int* out_count, float* feats_out, void* out_split, long long out_plane, tt_stream_t stream) {
+  TT_REQUIRE(d && feats_in_split && w_split && pairs_in && pairs_out && pair_count && out_count && feats_out, "tt_sparse_conv_f16s", "null argument");
+  if (d->Cin % 8 || d->Cout % 4 || d->in_ld % 8 || d->out_ld % 4 || d->Cin < 32 || d->Cout < 32 || d->kvol > MAX_KVOL || in_plane % 8 || out_plane % 4 ||
+      (d->res_ld % 4) ||
+      ((reinterpret_cast<uintptr_t>(feats_in_split) | reinterpret_cast<uintptr_t>(w_split) | reinterpret_cast<uintptr_t>(feats_out) |
+        reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(bias)) & 15) || (reinterpret_cast<uintptr_t>(out_split) & 7)) {
+    tt_set_error("tt_sparse_conv_f16s: needs Cin %% 8, Cout %% 4, Cin / Cout >= 32, in_ld %% 8, out_ld %% 4, 16-byte aligned pointers");
+    return TT_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->cap_out <= 0) return TT_OK;
+  const long long tot4 = (long long)d->cap_out * (d->Cout / 4);
+  const int nb = (int)((tot4 + 255) / 256 > 1184 ? 1184 : (tot4 + 255) / 256);
+  f16s_sparse_init_kernel<<<nb, 256, 0, st>>>(feats_out, d->out_ld, bias, d->Cout, out_count, d->cap_out);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_sparse_conv_f16s(init)");
+  HArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d.N = a.d.H = a.d.W = a.d.OH = a.d.OW = a.d.yH = a.d.yW = 1;
+  a.d.KH = a.d.KW = a.d.stride = a.d.dil = a.d.groups = 1;
+  a.d.oy_mul = a.d.ox_mul = 1;
+  a.d.Cin = d->Cin; a.d.x_ld = d->in_ld; a.d.Cout = d->Cout; a.d.y_ld = d->out_ld;
+  a.d.act = TT_ACT_NONE;
+  a.y = feats_out;
+  a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;
+  a.n_slabs = (d->Cin + KE - 1) / KE;
+  a.dbg = g_tt_debug & 0xFF;
+  a.gx = static_cast<const __half*>(feats_in_split); a.gx_plane = in_plane; a.gx_ld = d->in_ld;
+  a.pairs_in = pairs_in; a.pairs_out = pairs_out; a.pair_count = pair_count;
+  a.kvol = d->kvol; a.pair_cap = d->pair_cap;
+  a.splits = 1; a.k_per = a.n_slabs;
+  const int BN = d->Cout > 64 ? 128 : 64;
+  a.n_tiles = tt_cdiv(d->Cout, BN);
+  CUtensorMap mb;
+  if (!encode_weights(&mb, w_split, d->Cin, d->kvol, d->Cout, BN)) return TT_ERR_CUDA;
+  const int num_sms = num_sms_cached();
+  const long long cap_pairs = (long long)d->kvol * ((tt_cdiv(d->pair_cap, BM) + 1) / 2) * a.n_tiles;
+  const long long max_pairs = num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (cap_pairs < max_pairs ? cap_pairs : max_pairs)));
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, true>(cfg, mb, mb, a) : launch_f16s<64, 4, true>(cfg, mb, mb, a);
+  if (lerr != cudaSuccess) { tt_set_error("tt_sparse_conv_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_sparse_conv_f16s");
+  f16s_sparse_finish_kernel<<<nb, 256, 0, st>>>(feats_out, d->out_ld, res, d->res_ld, d->Cout, out_count, d->cap_out, d->act,
+                                                 static_cast<__half*>(out_split), out_plane);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_sparse_conv_f16s(finish)");
+  return TT_OK;
+}
+
+}  // extern "C"

@@ -96,7 +96,7 @@ class EncoderDecoder(nn.Module):
         if impl == lib.IMPL_AUTO:
             impl = lib.IMPL_3XTF32                                  # default engine: tcgen05 3xTF32 (fp32-class)
         self.eng = e = Engine(dev, impl)
-        pk = Packer(self.state_dict(), dev, tc_mode=impl if impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) else 0)
+        pk = Packer(self.state_dict(), dev, tc_mode=impl if impl in (lib.IMPL_TF32, lib.IMPL_3XTF32, lib.IMPL_F16S) else 0)
         self.img_encoder.prepare(pk, e)
         self.lidar_encoder.prepare(pk, e)
         self.decoder.prepare(pk, e, self)
@@ -130,7 +130,7 @@ class EncoderDecoder(nn.Module):
         f10 = self.se_block(e.conv(f21, w['conv21_10'], name=tag + '.c10', stride=2, act=ACT_RELU), w['MLP10'], tag + '.m10')
         f4 = self.se_block(e.conv(f10, w['conv10_4'], name=tag + '.c4', stride=2, act=ACT_RELU), w['MLP4'], tag + '.m4')
         f2 = self.se_block(e.conv(f4, w['conv4_2'], name=tag + '.c2', act=ACT_RELU), w['MLP2'], tag + '.m2')
-        flat_in = FMap(f2.t, f2.N, 1, 1, f2.H * f2.W * f2.C)           # channels-last flatten (weights re-indexed)
+        flat_in = f2.view(f2.N, 1, 1, f2.H * f2.W * f2.C)              # channels-last flatten (weights re-indexed)
         h = e.linear(flat_in, w['fc0'], name=tag + '.fc0', act=ACT_RELU)
         return e.linear(h, w['fc3'], name=tag + '.flat', act=ACT_RELU), [f10, f4, f2]
 

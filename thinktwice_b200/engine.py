@@ -14,23 +14,30 @@ from .lib import ConvDesc, _p, _stream
 
 class FMap:
     """A logical (N, H, W, C) fp32 tensor stored channels-last inside a buffer whose pixels hold `ld`
-    floats; the C channels start at `coff`.  Concat = several FMaps viewing one buffer."""
-    __slots__ = ('t', 'N', 'H', 'W', 'C', 'ld', 'coff')
+    floats; the C channels start at `coff`.  Concat = several FMaps viewing one buffer.
+    `s` (optional) is the buffer's scaled-split fp16 companion: two half planes (hi, lo') over the SAME element grid as
+    `t` (csrc/gemm_conv_f16s.cu), kept in step with `t` by whichever Engine op writes the map."""
+    __slots__ = ('t', 'N', 'H', 'W', 'C', 'ld', 'coff', 's')
 
-    def __init__(self, t, N, H, W, C, ld=None, coff=0):
+    def __init__(self, t, N, H, W, C, ld=None, coff=0, s=None):
         self.t, self.N, self.H, self.W, self.C = t, N, H, W, C
         self.ld = ld if ld is not None else C
         self.coff = coff
+        self.s = s
 
     def slice(self, coff, C):
-        return FMap(self.t, self.N, self.H, self.W, C, self.ld, self.coff + coff)
+        return FMap(self.t, self.N, self.H, self.W, C, self.ld, self.coff + coff, self.s)
+
+    def view(self, N, H, W, C, ld=None, coff=None):
+        """another geometry over the same storage (fp32 buffer and split companion)."""
+        return FMap(self.t, N, H, W, C, ld if ld is not None else C, self.coff if coff is None else coff, self.s)
 
     def rows(self):
         return self.N * self.H * self.W
 
     def as_rows(self):
         """view as a (rows, 1, 1, C) map (for Linear layers)."""
-        return FMap(self.t, self.rows(), 1, 1, self.C, self.ld, self.coff)
+        return FMap(self.t, self.rows(), 1, 1, self.C, self.ld, self.coff, self.s)
 
     def dense(self):
         """contiguous (N, H, W, C) torch view/copy of the logical tensor (debug / tests / outputs)."""
@@ -41,13 +48,19 @@ class FMap:
         return self.dense().permute(0, 3, 1, 2)
 
 
+def _ps(fm):
+    """device pointer of the hi plane of `fm`'s split companion at the map's channel offset (+ the plane stride in halves)."""
+    return _p(fm.s, fm.coff), fm.s.numel() // 2
+
+
 class PackedConv:
     """weights of one conv / linear in kernel layout: w [taps*Cin_g][Cout] (BatchNorm folded), bias [Cout]|None."""
-    __slots__ = ('w', 'bias', 'Cin', 'Cout', 'KH', 'KW', 'groups', 'w_tc', 'alg_k')
+    __slots__ = ('w', 'bias', 'Cin', 'Cout', 'KH', 'KW', 'groups', 'w_tc', 'w_h', 'alg_k')
 
-    def __init__(self, w, bias, Cin, Cout, KH=1, KW=1, groups=1, w_tc=None):
+    def __init__(self, w, bias, Cin, Cout, KH=1, KW=1, groups=1, w_tc=None, w_h=None):
         self.w, self.bias, self.Cin, self.Cout, self.KH, self.KW, self.groups = w, bias, Cin, Cout, KH, KW, groups
-        self.w_tc = w_tc            # [2][Cout][taps][Cin] TF32 hi / lo planes for the tcgen05 path (or None)
+        self.w_tc = w_tc            # [2][Cout][taps][Cin] TF32 hi / lo planes for the tcgen05 3xTF32 path (or None)
+        self.w_h = w_h              # [2][Cout][taps][Cin8] scaled-split fp16 planes for the tcgen05 f16s path (or None)
         self.alg_k = None           # algorithmic K per output (row-packed convs carry zero-weight padding)
 
 
@@ -103,6 +116,8 @@ class Engine:
         self.marks = None           # bench.py: list of (segment name, event) recorded by mark() in a serial eager step
         self.tc_min_rows = 512
         self.tc_strides = (1, 2)
+        self.split = impl == lib.IMPL_F16S   # feature maps carry a scaled-split fp16 companion (gemm_conv_f16s.cu)
+        self.stats = {'late_split': 0}
         self.prof = None            # bench.py: list of (name, flops, start_event, end_event) per conv launch
         lib.load()
 
@@ -149,14 +164,45 @@ class Engine:
         except KeyError:
             raise KeyError(f'static buffer {name} has not been staged') from None
 
-    def fmap(self, name, N, H, W, C, ld=None, zero=False):
+    def fmap(self, name, N, H, W, C, ld=None, zero=False, split=None):
         ld = ld if ld is not None else C
-        return FMap(self.buf(name, (N, H, W, ld), zero=zero), N, H, W, C, ld, 0)
+        t = self.buf(name, (N, H, W, ld), zero=zero)
+        want = self.split if split is None else (split and self.split)
+        # a tensor-core conv needs >= 128 GEMM rows: smaller maps only ever feed the SIMT kernels
+        sc = self.buf(name + '#s', (2, N * H * W * ld), torch.float16, zero=True) if want and ld % 4 == 0 and ld >= 32 and N * H * W >= 128 else None
+        return FMap(t, N, H, W, C, ld, 0, sc)
 
     def wrap(self, t, C=None):
         """wrap an existing contiguous (N, H, W, ld) tensor."""
         N, H, W, ld = t.shape
         return FMap(t, N, H, W, C if C is not None else ld, ld, 0)
+
+    # ------------------------------------------------------------------ scaled-split companions
+    def sync_split(self, fm):
+        """bring the split companion of `fm` in step with its fp32 values (after a non-convolution kernel wrote them)."""
+        if fm.s is None:
+            return fm
+        # the converter works on 4-column groups: widen the column range to the enclosing groups (the companion mirrors the
+        # fp32 buffer element for element, so converting a neighbour's columns as well is always consistent)
+        c0 = fm.coff // 4 * 4                                     # (coff may exceed ld: an element offset into the buffer)
+        w = -(-(fm.coff - c0 + fm.C) // 4) * 4
+        w = min(w, fm.ld - c0 % fm.ld) if fm.ld >= 4 else w
+        if fm.ld % 4 or w % 4 or w <= 0:
+            raise lib.TTError(f'split companion of a map with C={fm.C} coff={fm.coff} ld={fm.ld}: row pitch must be a multiple of 4')
+        lib.call('tt_split_f16', _p(fm.t, c0), C.c_longlong(fm.ld), _p(fm.s, c0), C.c_longlong(fm.s.numel() // 2), C.c_longlong(fm.ld),
+                 C.c_longlong(fm.rows()), w, None)
+        return fm
+
+    def with_split(self, fm):
+        """`fm` with a valid split companion: its own, or a late one (allocated per underlying buffer, converted now)."""
+        if fm.s is not None:
+            return fm
+        key = ('late#s', fm.t.data_ptr(), fm.t.numel())
+        sc = self.bufs.get(key)
+        if sc is None:
+            sc = self.bufs[key] = torch.zeros((2, fm.t.numel()), dtype=torch.float16, device=self.device)
+        self.stats['late_split'] += 1
+        return self.sync_split(FMap(fm.t, fm.N, fm.H, fm.W, fm.C, fm.ld, fm.coff, sc))
 
     # ------------------------------------------------------------------ conv / linear
     def conv(self, x, pw, out=None, name=None, stride=1, pad=0, dil=1, act=0, res=None, res_mode=0, res2=None,
@@ -190,16 +236,20 @@ class Engine:
         if res2 is not None:
             d.res2_ld, d.res2_coff = res2.ld, 0
         impl = self.impl if impl is None else impl
-        # tcgen05 path: dense stride-1 convs with enough work to fill 128-row tiles; everything else stays SIMT fp32
-        use_tc = (impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and stride in self.tc_strides and pw.groups == 1
-                  and x.ld % 4 == 0 and x.coff % 4 == 0 and out.ld % 4 == 0 and out.coff % 4 == 0
+        # tcgen05 paths: dense convs with enough work to fill 128-row tiles; everything else stays SIMT fp32
+        big = (d.N * OH * OW >= self.tc_min_rows or (d.N * OH * OW >= 128 and pw.KH * pw.KW * pw.Cin >= 2048))   # thin M: only with a long K (split-K)
+        common = (stride in self.tc_strides and pw.groups == 1 and out.ld % 4 == 0 and out.coff % 4 == 0
                   and (res is None or (res.ld % 4 == 0 and res.coff % 4 == 0)) and (res2 is None or (res2.ld % 4 == 0 and res2.coff % 4 == 0))
-                  and x_nstride % 4 == 0 and y_nstride % 4 == 0 and x_hstride % 4 == 0
-                  and (d.N * OH * OW >= self.tc_min_rows or (d.N * OH * OW >= 128 and pw.KH * pw.KW * pw.Cin >= 2048))   # thin M: only with a long K (split-K)
-                  and pw.Cout >= 32)
-        d.impl = impl if use_tc else lib.IMPL_SIMT
+                  and y_nstride % 4 == 0 and big and pw.Cout >= 32)
+        use_h = (impl == lib.IMPL_F16S and pw.w_h is not None and common and x.ld % 8 == 0 and x.coff % 8 == 0 and x_nstride % 8 == 0
+                 and x_hstride % 8 == 0 and (x.s is not None or (x.C % 4 == 0 and x.t is not None)))
+        use_tc = (impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and common and x.ld % 4 == 0 and x.coff % 4 == 0
+                  and x_nstride % 4 == 0 and x_hstride % 4 == 0)
+        d.impl = impl if (use_tc or use_h) else lib.IMPL_SIMT
+        if use_h:
+            xs = self.with_split(x)
         ws = None
-        need = lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # SIMT: split-K partials; tcgen05: 0
+        need = 0 if use_h else lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # SIMT: split-K partials; tcgen05: 0
         if need:
             ws = self.conv_ws.get(self.lane)
             if ws is None or ws.numel() < need:
@@ -209,10 +259,22 @@ class Engine:
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        lib.check(lib.load().tt_conv2d(
-            C.byref(d), _p(x.t, x.coff), _p(pw.w_tc if use_tc else pw.w), _p(pw.bias),
-            _p(res.t, res.coff) if res is not None else None, _p(res2.t, res2.coff) if res2 is not None else None,
-            None, None, _p(out.t, out.coff), _p(ws), _stream()), f'tt_conv2d[{name}]')
+        pres = _p(res.t, res.coff) if res is not None else None
+        pres2 = _p(res2.t, res2.coff) if res2 is not None else None
+        if use_h:
+            px, xplane = _ps(xs)
+            pys, yplane = _ps(out) if out.s is not None else (None, 0)
+            lib.check(lib.load().tt_conv2d_f16s(C.byref(d), px, C.c_longlong(xplane), _p(pw.w_h), _p(pw.bias), pres, pres2,
+                                                _p(out.t, out.coff), pys, C.c_longlong(yplane), _stream()), f'tt_conv2d_f16s[{name}]')
+        else:
+            lib.check(lib.load().tt_conv2d(
+                C.byref(d), _p(x.t, x.coff), _p(pw.w_tc if use_tc else pw.w), _p(pw.bias), pres, pres2,
+                None, None, _p(out.t, out.coff), _p(ws), _stream()), f'tt_conv2d[{name}]')
+            if out.s is not None:
+                if y_nstride or scatter is not None:                  # strided / scattered rows: refresh the whole buffer's companion
+                    self.sync_split(FMap(out.t, out.t.numel() // out.ld, 1, 1, out.ld, out.ld, 0, out.s))
+                else:
+                    self.sync_split(out)
         if self.prof is not None:
             ev1.record()
             flops = 2.0 * d.N * OH * OW * (pw.alg_k or pw.KH * pw.KW * pw.Cin // pw.groups) * pw.Cout
@@ -228,21 +290,40 @@ class Engine:
             out = out.as_rows()
         return self.conv(xr, pw, out=out, name=name, act=act, res=res.as_rows() if res is not None else None)
 
-    def sparse_conv(self, feats, pw, rule, out, act=0, res=None, name=None):
-        """tap-major sparse conv over a rulebook `rule` (dict from LidarNet._rulebook): feats [cap_in][Cin] -> out [cap_out][Cout]."""
+    def sparse_feats(self, name, rows, Cc):
+        """(fp32 rows [rows][C], split companion [2][rows*C] or None) for a sparse feature matrix."""
+        t = self.buf(name, (rows, Cc))
+        sc = self.buf(name + '#s', (2, rows * Cc), torch.float16, zero=True) if self.split and Cc % 8 == 0 and Cc >= 32 else None
+        return t, sc
+
+    def sparse_conv(self, feats, pw, rule, out, act=0, res=None, name=None, feats_s=None, out_s=None):
+        """tap-major sparse conv over a rulebook `rule` (dict from LidarNet._rulebook): feats [cap_in][Cin] -> out [cap_out][Cout].
+        feats_s / out_s: scaled-split companions of the input / output rows (f16s engine)."""
         d = lib.SparseConvDesc()
         d.Cin, d.Cout, d.kvol = pw.Cin, pw.Cout, rule['kvol']
         d.in_ld, d.out_ld, d.res_ld = feats.shape[1], out.shape[1], (res.shape[1] if res is not None else 0)
         d.cap_out, d.pair_cap, d.act = rule['cap'], rule['cap'], act
-        use_tc = (self.impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and pw.Cin >= 32 and pw.Cout >= 32
-                  and pw.Cin % 4 == 0 and d.in_ld % 4 == 0 and d.out_ld % 4 == 0 and rule['kvol'] <= 32)
-        d.impl = self.impl if use_tc else lib.IMPL_SIMT
+        wide = pw.Cin >= 32 and pw.Cout >= 32 and rule['kvol'] <= 32
+        use_h = (self.impl == lib.IMPL_F16S and pw.w_h is not None and feats_s is not None and wide and pw.Cin % 8 == 0 and d.in_ld % 8 == 0
+                 and d.out_ld % 4 == 0)
+        use_tc = (self.impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and wide
+                  and pw.Cin % 4 == 0 and d.in_ld % 4 == 0 and d.out_ld % 4 == 0)
+        d.impl = self.impl if (use_tc or use_h) else lib.IMPL_SIMT
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        lib.check(lib.load().tt_sparse_conv(C.byref(d), _p(feats), _p(pw.w_tc if use_tc else pw.w), _p(pw.bias), _p(res), _p(rule['pairs_in']),
-                                            _p(rule['pairs_out']), _p(rule['pair_count']), _p(rule['count']), _p(out),
-                                            _stream()), f'tt_sparse_conv[{name}]')
+        if use_h:
+            lib.check(lib.load().tt_sparse_conv_f16s(C.byref(d), _p(feats_s), C.c_longlong(feats_s.numel() // 2), _p(pw.w_h), _p(pw.bias), _p(res),
+                                                     _p(rule['pairs_in']), _p(rule['pairs_out']), _p(rule['pair_count']), _p(rule['count']), _p(out),
+                                                     _p(out_s), C.c_longlong(out_s.numel() // 2 if out_s is not None else 0), _stream()),
+                      f'tt_sparse_conv_f16s[{name}]')
+        else:
+            lib.check(lib.load().tt_sparse_conv(C.byref(d), _p(feats), _p(pw.w_tc if use_tc else pw.w), _p(pw.bias), _p(res), _p(rule['pairs_in']),
+                                                _p(rule['pairs_out']), _p(rule['pair_count']), _p(rule['count']), _p(out),
+                                                _stream()), f'tt_sparse_conv[{name}]')
+            if out_s is not None:                                    # rows produced by the SIMT kernel: convert the first *count of them
+                lib.call('tt_split_f16', _p(out), C.c_longlong(out.shape[1]), _p(out_s), C.c_longlong(out_s.numel() // 2), C.c_longlong(out.shape[1]),
+                         C.c_longlong(out.shape[0]), out.shape[1], _p(rule['count']))
         if self.prof is not None:
             ev1.record()
             self.prof.append((f'sparse.{name}', 0.0, ev0, ev1))    # data-dependent work: algorithmic FLOPs not counted
@@ -254,7 +335,7 @@ class Engine:
         cpad = cpad or Cc
         out = self.fmap(name, N, H, W, cpad)
         lib.call('tt_nchw_to_nhwc', _p(x), _p(out.t), N, Cc, H, W, out.ld, 0, cpad)
-        return out
+        return self.sync_split(out)
 
     def nchw_to_nhwc_padded(self, x, name, cpad, top, bottom, left, right):
         """NCHW -> channels-last inside a zero-bordered [N][top+H+bottom][left+W+right][cpad] buffer (zeroed once at
@@ -273,34 +354,34 @@ class Engine:
         assert x.ld == x.C and x.coff == 0
         out = self.fmap(name, x.N, (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1, x.C)
         lib.call('tt_maxpool3x3s2', _p(x.t), _p(out.t), x.N, x.H, x.W, x.C)
-        return out
+        return self.sync_split(out)
 
     def upsample2x(self, x, name):
         assert x.ld == x.C and x.coff == 0
         out = self.fmap(name, x.N, 2 * x.H, 2 * x.W, x.C)
         lib.call('tt_upsample2x_bilinear_ac', _p(x.t), _p(out.t), x.N, x.H, x.W, x.C)
-        return out
+        return self.sync_split(out)
 
     def global_avgpool(self, x, name):
         out = self.fmap(name, x.N, 1, 1, x.C)
         lib.call('tt_global_avgpool', _p(x.t, x.coff), x.ld, 0, _p(out.t), x.N, x.H * x.W, x.C)
-        return out
+        return self.sync_split(out)
 
     def broadcast_rows(self, v, out):
         lib.call('tt_broadcast_rows', _p(v.t, v.coff), _p(out.t, out.coff), out.N, out.H * out.W, out.C, out.ld, 0)
-        return out
+        return self.sync_split(out)
 
     def se_gate(self, x, g, name):
         assert x.ld == x.C and x.coff == 0 and g.ld == g.C
         out = self.fmap(name, x.N, x.H, x.W, x.C)
         lib.call('tt_se_gate', _p(x.t), _p(g.t), _p(out.t), x.N, x.H * x.W, x.C)
-        return out
+        return self.sync_split(out)
 
     def se_pool(self, x, name):
         assert x.ld == x.C and x.coff == 0
         out = self.fmap(name, x.N, 1, 1, x.C)
         lib.call('tt_se_pool', _p(x.t), _p(out.t), x.N, x.H * x.W, x.C)
-        return out
+        return self.sync_split(out)
 
     def se_apply(self, x, g, shortcut, out=None, name=None):
         assert x.ld == x.C and x.coff == 0
@@ -308,13 +389,13 @@ class Engine:
             out = self.fmap(name, x.N, x.H, x.W, x.C)
         lib.call('tt_se_apply', _p(x.t), _p(g.t), _p(shortcut.t, shortcut.coff), shortcut.ld, 0, _p(out.t, out.coff),
                  out.ld, 0, x.N, x.H * x.W, x.C)
-        return out
+        return self.sync_split(out)
 
     def anti_transpose(self, x, name):
         assert x.ld == x.C and x.coff == 0 and x.H == x.W
         out = self.fmap(name, x.N, x.H, x.W, x.C)
         lib.call('tt_anti_transpose', _p(x.t), _p(out.t), x.N, x.H, x.C)
-        return out
+        return self.sync_split(out)
 
     def copy_cols(self, src, dst, rdiv=1, rmod=None):
         """dst rows r (all pixels of dst) <- src row (r // rdiv) % rmod; copies src.C columns."""
@@ -322,7 +403,7 @@ class Engine:
         rmod = rmod if rmod is not None else max(src.rows(), 1)
         assert src.C == dst.C
         lib.call('tt_copy2d', _p(src.t, src.coff), src.ld, _p(dst.t, dst.coff), dst.ld, rows, src.C, rdiv, rmod)
-        return dst
+        return self.sync_split(dst)
 
     def layernorm(self, x, gamma, beta, out=None, name=None, out_ld=None, row_count=None):
         xr = x.as_rows()
@@ -330,7 +411,7 @@ class Engine:
             out = self.fmap(name, xr.N, 1, 1, xr.C, out_ld, zero=True)
         lib.call('tt_layernorm', _p(xr.t, xr.coff), xr.ld, _p(gamma), _p(beta), _p(out.t, out.coff), out.ld, xr.N, xr.C,
                  _p(row_count))
-        return out
+        return self.sync_split(out)
 
     def eltwise(self, op, a, b=None, c=None, out=None, name=None, act=0):
         a_, b_, c_ = a.as_rows(), (b.as_rows() if b is not None else None), (c.as_rows() if c is not None else None)
@@ -339,7 +420,7 @@ class Engine:
         o_ = out.as_rows()
         lib.call('tt_eltwise', op, act, _p(a_.t, a_.coff), a_.ld, _p(b_.t, b_.coff) if b_ else None, b_.ld if b_ else 0,
                  _p(c_.t, c_.coff) if c_ else None, c_.ld if c_ else 0, _p(o_.t, o_.coff), o_.ld, a_.N, a_.C)
-        return out
+        return self.sync_split(out)
 
     def fill(self, t, v=0.0):
         lib.call('tt_fill', _p(t), C.c_float(v), C.c_longlong(t.numel()))

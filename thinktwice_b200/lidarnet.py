@@ -133,27 +133,35 @@ class LidarNet(nn.Module):
         shape = self.me.sparse_shape
         # conv_input (SubM 5 -> 16); all SubM convs of one resolution share one rulebook (spconv indice_key)
         rb = self._rulebook('l0', B, coords, count, cap, shape, self.k_in, (1, 1, 1), (1, 1, 1), True)
-        x = e.sparse_conv(feats, self.w_in, rb, e.buf('sp.l0.x', (rb['cap'], self.w_in.Cout)), act=ACT_RELU, name='conv_input')
+        x, xs = e.sparse_feats('sp.l0.x', rb['cap'], self.w_in.Cout)
+        e.sparse_conv(feats, self.w_in, rb, x, act=ACT_RELU, name='conv_input', out_s=xs)
         for i, st in enumerate(self.stages):
             for j, layer in enumerate(st):
                 if layer[0] == 'block':
                     _, w1, w2 = layer
-                    t = e.sparse_conv(x, w1, rb, e.buf(f'sp.l{i}.t', (rb['cap'], w1.Cout)), act=ACT_RELU, name=f'{i}.{j}.conv1')
-                    x = e.sparse_conv(t, w2, rb, e.buf(f'sp.l{i}.o{j % 2}', (rb['cap'], w2.Cout)), act=ACT_RELU, res=x, name=f'{i}.{j}.conv2')
+                    t, ts = e.sparse_feats(f'sp.l{i}.t', rb['cap'], w1.Cout)
+                    e.sparse_conv(x, w1, rb, t, act=ACT_RELU, name=f'{i}.{j}.conv1', feats_s=xs, out_s=ts)
+                    o, os_ = e.sparse_feats(f'sp.l{i}.o{j % 2}', rb['cap'], w2.Cout)
+                    e.sparse_conv(t, w2, rb, o, act=ACT_RELU, res=x, name=f'{i}.{j}.conv2', feats_s=ts, out_s=os_)
+                    x, xs = o, os_
                 else:
                     _, wc, k, s, p = layer
                     rd = self._rulebook(f'd{i}', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], k, s, p, False)
-                    x = e.sparse_conv(x, wc, rd, e.buf(f'sp.l{i + 1}.x', (rd['cap'], wc.Cout)), act=ACT_RELU, name=f'{i}.{j}.down')
+                    o, os_ = e.sparse_feats(f'sp.l{i + 1}.x', rd['cap'], wc.Cout)
+                    e.sparse_conv(x, wc, rd, o, act=ACT_RELU, name=f'{i}.{j}.down', feats_s=xs, out_s=os_)
+                    x, xs = o, os_
                     # rulebook of the SubM convs at the new resolution
                     rb = self._rulebook(f'l{i + 1}', B, rd['coords'], rd['count'], rd['cap'], rd['shape'], (3, 3, 3), (1, 1, 1), (1, 1, 1), True)
         ro = self._rulebook('out', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], self.k_out, (2, 1, 1), (0, 0, 0), False)
-        x = e.sparse_conv(x, self.w_out, ro, e.buf('sp.out.x', (ro['cap'], self.w_out.Cout)), act=ACT_RELU, name='conv_out')
+        o, _ = e.sparse_feats('sp.out.x', ro['cap'], self.w_out.Cout)
+        x = e.sparse_conv(x, self.w_out, ro, o, act=ACT_RELU, name='conv_out', feats_s=xs)
         coords2, count2, cap2, shape2 = ro['coords'], ro['count'], ro['cap'], ro['shape']
         D, H, W = shape2
         Cs = self.w_out.Cout
         dense = e.fmap('lidar.dense', B, H, W, Cs * D)
         e.fill(dense.t, 0.0)
         lib.call('tt_sparse_to_bev', _p(x), _p(coords2), _p(count2), cap2, Cs, D, H, W, 0, _p(dense.t))
+        e.sync_split(dense)
         return self._second(dense)
 
     def _second(self, x):

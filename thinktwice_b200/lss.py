@@ -53,7 +53,10 @@ class LSS(nn.Module):
         p = self.prefix
         w = self.w = {}
         b = p + 'img_backbone.'
-        w['stem'] = pk.conv_rowpacked(b + 'conv1', bn=b + 'bn1', cpad=4, kslab=32)   # 7x7x3 s2: 7 row-packed K slabs
+        if pk.tc_mode == 4:                                          # f16s engine: 8 halves per pixel, 64-half K slabs
+            w['stem'] = pk.conv_rowpacked(b + 'conv1', bn=b + 'bn1', cpad=8, kslab=64)
+        else:
+            w['stem'] = pk.conv_rowpacked(b + 'conv1', bn=b + 'bn1', cpad=4, kslab=32)   # 7x7x3 s2: 7 row-packed K slabs
         self.blocks = []
         for li, n in enumerate([3, 4, 6, 3]):
             for i in range(n):
@@ -191,6 +194,7 @@ class LSS(nn.Module):
         off = e.conv(y, w['dcn_off'], name='dn.dcn.off', pad=1)
         col = e.fmap('dn.dcn.col', BN, H, W, 9 * self.mid)
         lib.call('tt_dcn_im2col', _p(y.t), _p(off.t), off.ld, _p(col.t), BN, H, W, self.mid, 4)
+        e.sync_split(col)
         yd = e.fmap('dn.dcn.out', BN, H, W, self.mid)
         cg = 9 * self.mid // len(w['dcn'])
         for g, wg in enumerate(w['dcn']):                               # grouped conv = one dense GEMM per group slice
@@ -241,8 +245,17 @@ class LSS(nn.Module):
         H0, W0 = im.shape[2:]
         pb = e.nchw_to_nhwc_padded(im, 'img.nhwc', 4, 3, 3, 3, 5)
         Wp = W0 + 8
-        x = e.conv(FMap(pb, B * N, H0 + 6, W0, 32, ld=4), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
-                   x_hstride=Wp * 4, x_nstride=(H0 + 6) * Wp * 4)
+        if e.split:
+            # scaled-split engine: 8 halves per pixel (3 channels + 5 zeros; TMA strides are multiples of 16 bytes), so a tap row
+            # of 7 px is 56 halves inside ONE 64-half K slab; the companion is zeroed once, only channels 0..3 are ever written
+            rows = B * N * (H0 + 6) * Wp
+            pbs = e.buf('img.nhwc#s8', (2, rows * 8), torch.float16, zero=True)
+            lib.call('tt_split_f16', _p(pb), C.c_longlong(4), _p(pbs), C.c_longlong(rows * 8), C.c_longlong(8), C.c_longlong(rows), 4, None)
+            x = e.conv(FMap(None, B * N, H0 + 6, W0, 64, ld=8, s=pbs), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
+                       x_hstride=Wp * 8, x_nstride=(H0 + 6) * Wp * 8)
+        else:
+            x = e.conv(FMap(pb, B * N, H0 + 6, W0, 32, ld=4), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
+                       x_hstride=Wp * 4, x_nstride=(H0 + 6) * Wp * 4)
         fpn = self._pafpn(self._backbone(x))
         src = e.conv(fpn[2], w['neck_conv'], name='img_feats')
         mlp_in = e.wrap(e.static('in.mlp_in').view(B * N, 1, 1, 24))
@@ -261,6 +274,7 @@ class LSS(nn.Module):
         ws = e.buf('lift.ws', (lib.load().tt_lift_splat_workspace_bytes(C.byref(d)),), dtype=torch.uint8)
         lib.call('tt_lift_splat', C.byref(d), _p(depth.t), _p(feat.t), _p(m), _p(self.fu), _p(self.fv), _p(self.fd),
                  _p(bev_out.t, bev_out.coff), _p(ws))
+        e.sync_split(bev_out)
         return dict(fpn_feats=fpn, depth=depth, seg=seg, img_feature=feat)
 
     # ------------------------------------------------------------------ forward (lss.py:635-724)

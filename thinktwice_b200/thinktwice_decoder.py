@@ -135,13 +135,14 @@ class ThinkTwiceDecoder(nn.Module):
         for t in range(T):
             for buf in (xs, cin):
                 lib.call('tt_gru_input', _p(wp.t), _p(ctrl_sp.t), t, T, _p(buf.t, 32), buf.ld, B, HW)
+                e.sync_split(buf.slice(32, 8))
             u = e.conv(e.conv(xs, L['conv_update'][0], name='gru.u1', pad=1, act=ACT_RELU), L['conv_update'][1], name='gru.u', pad=1, act=ACT_SIGMOID)
             r = e.conv(e.conv(xs, L['conv_reset'][0], name='gru.r1', pad=1, act=ACT_RELU), L['conv_reset'][1], name='gru.r', pad=1, act=ACT_SIGMOID)
             e.eltwise(1, r, state, out=cin.slice(0, Cs))             # (1 - r) * state
             cand = e.conv(e.conv(cin, L['conv_state_tilde'][0], name='gru.c1', pad=1, act=ACT_RELU), L['conv_state_tilde'][1], name='gru.c', pad=1)
             e.eltwise(2, u, state, cand, out=state)                  # (1 - u) * state + u * cand
             d1 = e.conv(state, L['conv_decoder'][0], name='gru.d1', pad=1, act=ACT_RELU)
-            out_t = FMap(fut.t, B, H, W, Cs, Cs, t * HW * Cs)        # image b of step t lives at index b*T + t
+            out_t = fut.view(B, H, W, Cs, Cs, t * HW * Cs)           # image b of step t lives at index b*T + t
             e.conv(d1, L['conv_decoder'][1], out=out_t, name='gru.d', pad=1, y_nstride=T * HW * Cs)
         return fut
 
@@ -162,7 +163,7 @@ class ThinkTwiceDecoder(nn.Module):
                  ptrs, _p(ref_cam), _p(order), _p(counts), _p(rows.t), rows.ld, _p(ref_re))
         # query_linear: LN(1543) -> 512 GELU -> 256 GELU (msda:251-257)
         q = e.layernorm(rows, *L['q_ln'], name='look.q_ln', out_ld=1544)
-        q = e.linear(FMap(q.t, q.N, 1, 1, 1544), L['q1'], name='look.q1', act=ACT_GELU)
+        q = e.linear(q.view(q.N, 1, 1, 1544), L['q1'], name='look.q1', act=ACT_GELU)
         q = e.linear(q, L['q3'], name='look.q', act=ACT_GELU)
         # value_proj over all keys of every (cam, level) with the embedding folded into the bias (msda:474)
         nk = meta['num_keys']
@@ -234,7 +235,7 @@ class ThinkTwiceDecoder(nn.Module):
             ci = e.fmap('dec.ctrl_in', B * T, 1, 1, 516); e.copy_cols(ctrl, ci.slice(0, 4)); e.copy_cols(a, ci.slice(4, 512))
             t_off = self._seq(ti, L['traj'], 'dec.toff')
             c_off = self._seq(ci, L['ctrl'], 'dec.coff')
-            a_flat = FMap(a.t, B, 1, 1, T * 512)
+            a_flat = a.view(B, 1, 1, T * 512)
             # BEV update (thinktwice_decoder.py:257): conv over [BEV 32 | all_future 2048 tiled] + residual
             bi = e.fmap('dec.bev_in', B, cur_bev.H, cur_bev.W, 32 + T * 512)
             e.copy_cols(cur_bev, bi.slice(0, 32)); e.copy_cols(a_flat, bi.slice(32, T * 512), rdiv=cur_bev.H * cur_bev.W)

@@ -29,11 +29,25 @@ def tf32_split(w, rn=True):
     return hi, _rn_tf32(w - hi)
 
 
+F16S_SCALE = 2048.0
+
+
+def f16s_split(w):
+    """w (fp32 / fp64) -> (hi, lo') halves with hi = RN_f16(w), lo' = RN_f16((w - hi) * 2048): the scaled-split operand format of
+    csrc/gemm_conv_f16s.cu (w = hi + lo' / 2048 to 2^-22 relative).  Weights must lie inside the fp16 range."""
+    w = w.float().contiguous()
+    if w.numel() and float(w.abs().max()) > 65504.0:
+        raise ValueError('f16s weight packing: |w| exceeds the fp16 range')
+    hi = w.half()
+    lo = ((w - hi.float()) * F16S_SCALE).half()
+    return hi, lo
+
+
 class Packer:
     def __init__(self, sd, device, tc_mode=0):
         self.sd = {k: v.detach().cpu() for k, v in sd.items()}
         self.device = device
-        self.tc_mode = tc_mode      # 0: SIMT only; 2 / 3: also pack [2][Cout][taps][Cin] TF32 hi/lo planes for tcgen05
+        self.tc_mode = tc_mode      # 0: SIMT only; 2 / 3: also pack [2][Cout][taps][Cin] TF32 hi/lo planes; 4: scaled-split fp16 planes
 
     def _tc(self, w_ohwi):
         """w_ohwi: (Cout, taps, Cin) float64 -> device tensor [2][Cout][taps][Cin] or None."""
@@ -41,6 +55,18 @@ class Packer:
         if self.tc_mode not in (2, 3) or Cin % 4 or Cout % 4 or Cout < 32:
             return None
         hi, lo = tf32_split(w_ohwi.float())
+        return torch.stack([hi, lo]).contiguous().to(self.device)
+
+    def _h(self, w_ohwi):
+        """w_ohwi: (Cout, taps, Cin) float64 -> device tensor [2][Cout][taps][Cin8] halves (Cin zero-padded to 8) or None."""
+        Cout, taps, Cin = w_ohwi.shape
+        if self.tc_mode != 4 or Cout % 4 or Cout < 32:
+            return None
+        c8 = -(-Cin // 8) * 8
+        w = w_ohwi.float()
+        if c8 != Cin:
+            w = torch.cat([w, w.new_zeros(Cout, taps, c8 - Cin)], 2)
+        hi, lo = f16s_split(w)
         return torch.stack([hi, lo]).contiguous().to(self.device)
 
     def _dev(self, t):
@@ -76,8 +102,9 @@ class Packer:
             w = torch.cat([w, w.new_zeros(Cout, cin_pad - Cg, KH, KW)], 1)
             Cg = cin_pad
         packed = w.permute(2, 3, 1, 0).reshape(KH * KW * Cg, Cout)
-        w_tc = self._tc(w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cg)) if groups == 1 else None
-        return PackedConv(self._dev(packed), self._dev(b), Cg * groups, Cout, KH, KW, groups, w_tc)
+        ohwi = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cg)
+        w_tc = self._tc(ohwi) if groups == 1 else None
+        return PackedConv(self._dev(packed), self._dev(b), Cg * groups, Cout, KH, KW, groups, w_tc, self._h(ohwi) if groups == 1 else None)
 
     def conv_rowpacked(self, n, bn=None, eps=1e-5, cpad=4, kslab=32):
         """thin-channel Conv2d (Cout, Cin<=cpad, KH, KW) [+BN] as a KH x 1 conv whose "channels" are the KW*cpad floats
@@ -96,7 +123,7 @@ class Packer:
         wk = w.new_zeros(Cout, KH, kslab)                                # [co][kh][kw * cpad + c]
         wk.view(Cout, KH, kslab // cpad, cpad)[:, :, :KW, :Cin] = w.permute(0, 2, 3, 1)
         pc = PackedConv(self._dev(wk.permute(1, 2, 0).reshape(KH * kslab, Cout)), self._dev(b), kslab, Cout, KH, 1,
-                        w_tc=self._tc(wk))
+                        w_tc=self._tc(wk), w_h=self._h(wk))
         pc.alg_k = KH * KW * Cin
         return pc
 
@@ -110,7 +137,8 @@ class Packer:
         out = []
         for g in range(groups):
             wg = w[g * Co:(g + 1) * Co].permute(0, 2, 3, 1).reshape(Co, KH * KW * Cg)      # K = (tap, cin)
-            out.append(PackedConv(self._dev(wg.t()), None, KH * KW * Cg, Co, w_tc=self._tc(wg.reshape(Co, 1, KH * KW * Cg))))
+            out.append(PackedConv(self._dev(wg.t()), None, KH * KW * Cg, Co, w_tc=self._tc(wg.reshape(Co, 1, KH * KW * Cg)),
+                                  w_h=self._h(wg.reshape(Co, 1, KH * KW * Cg))))
         return out
 
     def linear(self, n, bn_after=None, eps=1e-5, in_affine=None, cin_pad=None, weight=None, bias=None, cin_index=None):
@@ -135,7 +163,7 @@ class Packer:
         if cin_pad is not None and cin_pad > Cin:
             w = torch.cat([w, w.new_zeros(Cout, cin_pad - Cin)], 1)
             Cin = cin_pad
-        return PackedConv(self._dev(w.t()), self._dev(b), Cin, Cout, w_tc=self._tc(w.reshape(Cout, 1, Cin)))
+        return PackedConv(self._dev(w.t()), self._dev(b), Cin, Cout, w_tc=self._tc(w.reshape(Cout, 1, Cin)), w_h=self._h(w.reshape(Cout, 1, Cin)))
 
     def conv1x1_as_linear(self, n, **kw):
         w = self.sd[n + '.weight']
@@ -152,7 +180,8 @@ class Packer:
             b = t if b is None else b * s + t
         Cin, Cout = w.shape[:2]
         bd = self._dev(b)
-        return [[PackedConv(self._dev(w[:, :, i, j]), bd, Cin, Cout, w_tc=self._tc(w[:, :, i, j].t().reshape(Cout, 1, Cin)))
+        return [[PackedConv(self._dev(w[:, :, i, j]), bd, Cin, Cout, w_tc=self._tc(w[:, :, i, j].t().reshape(Cout, 1, Cin)),
+                            w_h=self._h(w[:, :, i, j].t().reshape(Cout, 1, Cin)))
                  for j in range(2)] for i in range(2)]
 
     def spconv(self, n, bn, eps=1e-3):
@@ -162,7 +191,8 @@ class Packer:
         w = w * s.view(-1, 1, 1, 1, 1)
         Cout, kd, kh, kw, Cin = w.shape
         packed = w.reshape(Cout, kd * kh * kw, Cin).permute(1, 2, 0).reshape(kd * kh * kw * Cin, Cout)
-        pc = PackedConv(self._dev(packed), self._dev(t), Cin, Cout, w_tc=self._tc(w.reshape(Cout, kd * kh * kw, Cin)) if Cin >= 32 else None)
+        pc = PackedConv(self._dev(packed), self._dev(t), Cin, Cout, w_tc=self._tc(w.reshape(Cout, kd * kh * kw, Cin)) if Cin >= 32 else None,
+                        w_h=self._h(w.reshape(Cout, kd * kh * kw, Cin)) if Cin >= 32 else None)
         return pc, (kd, kh, kw)
 
     def vec(self, n):
