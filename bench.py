@@ -145,8 +145,8 @@ def main():
     ap.add_argument('--no-latency', action='store_true', help='skip the extra B=1 latency measurement')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
     ap.add_argument('--dump-convs', default=None, help='write per-conv-launch (name, flops, ms) of one step to this JSON file')
-    ap.add_argument('--conv', default='3xtf32', choices=['simt', '3xtf32', 'tf32'],
-                    help='dense-conv engine: tcgen05 3xTF32 (fp32-class, default), tcgen05 single-pass TF32, or SIMT fp32')
+    ap.add_argument('--conv', default='f16s', choices=['simt', '3xtf32', 'tf32', 'f16s'],
+                    help='dense-conv engine: tcgen05 scaled-split fp16 (fp32-class, default), tcgen05 3xTF32, single-pass TF32, or SIMT fp32')
     ap.add_argument('--dbg', type=int, default=0, help='experiment: tt_debug_set knob bits (see csrc/gemm_conv_tc.cu)')
     ap.add_argument('--tc-reserve', type=int, default=0, help='experiment: SMs the persistent tcgen05 kernels leave free for the side branch')
     args = ap.parse_args()
@@ -190,7 +190,7 @@ def main():
     from thinktwice_b200.synthetic import make_batch
 
     model = build_model(cfg.model)
-    model.prepare(dev, impl={'simt': lib.IMPL_SIMT, '3xtf32': lib.IMPL_3XTF32, 'tf32': lib.IMPL_TF32}[args.conv])
+    model.prepare(dev, impl={'simt': lib.IMPL_SIMT, '3xtf32': lib.IMPL_3XTF32, 'tf32': lib.IMPL_TF32, 'f16s': lib.IMPL_F16S}[args.conv])
     B = args.batch
     host = make_batch(cfg, B, seed=100 + rank)                    # every rank owns different frames (weak scaling)
     for k in ('img', 'points', 'speed', 'target_point', 'target_command'):
@@ -249,6 +249,8 @@ def main():
     wp_eager = step(resident).float().cpu()
     parity = float((wp_timed - wp_eager).abs().max() / wp_eager.abs().max().clamp_min(1e-12))
     assert parity < 1e-3 and bool(torch.isfinite(wp_timed).all()), f'graph replay differs from the eager forward: {parity}'
+    saturated = model.f16s_saturations()
+    assert saturated == 0, f'{saturated} tensor-core operands left the fp16 range (scaled-split engine)'
 
     # ---- roofline of the dominant kernel family (implicit-GEMM conv): per-launch CUDA events on the launching stream
     model.eng.prof, model.eng.marks = [], []                     # per-launch events need eager, serial launches
@@ -298,7 +300,8 @@ def main():
     frames = args.steps * B * world
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     line = dict(base, value=frames / (ms * 1e-3), steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
-                dtype={'simt': 'f32', '3xtf32': 'f32 (3xTF32 tensor-core products, fp32 accumulate)', 'tf32': 'tf32'}[args.conv], gpu_launches=launches, clocks=summarize_clocks(samples),
+                dtype={'simt': 'f32', '3xtf32': 'f32 (3xTF32 tensor-core products, fp32 accumulate)', 'tf32': 'tf32',
+                       'f16s': 'f32 (operands as scaled-split fp16 pairs hi + lo/2048 = 22 mantissa bits, 3 tensor-core products, fp32 accumulate)'}[args.conv], gpu_launches=launches, clocks=summarize_clocks(samples),
                 e2e={'value': frames / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                      'd2h_bytes_per_step': B * 6 * 4 * 2 * 4},
                 roofline={'bound': 'tensor', 'kernel': 'conv_igemm (implicit-GEMM conv / linear family)',
@@ -311,7 +314,7 @@ def main():
                           'frac_lower_bound': conv_flops / (ms / args.steps * 1e-3) / 1e12 / tensor_peak,
                           'lower_bound_note': 'family FLOPs / the WHOLE timed (graph-replayed) step: what the family achieves at least'},
                 segments_ms_serial_eager=segments,
-                checks={'timed_mode_vs_eager_pred_wp_relerr': parity})
+                checks={'timed_mode_vs_eager_pred_wp_relerr': parity, 'f16s_saturated_operands': saturated})
     if lat is not None:
         line['latency_b1'] = {'ms_per_frame': lat, 'frames_per_s': 1000.0 / lat,
                               'note': 'configs[1]: one frame per forward (closed-loop mode), same model, CUDA-graph replay, inputs resident'}

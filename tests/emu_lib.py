@@ -182,6 +182,7 @@ class Emu:
         return 0
 
     def tt_f16s_saturation_count(self, out_host, reset, stream):
+        _desc(out_host).value = 0
         return 0
 
     # ------------------------------------------------------------------ LiDAR: voxelise, rulebooks, sparse conv, densify

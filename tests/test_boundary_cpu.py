@@ -107,12 +107,18 @@ def test_inputs_that_change_shape_between_calls_are_not_served_from_stale_buffer
     cfg, o, m, batch = _oracle_pair(1, 900, 0)
     m.prepare('cpu', impl=1)
     seq = [batch, make_batch(cfg, 1, seed=4, num_points=700), make_batch(cfg, 2, seed=6, num_points=1100)]
+    first = None
     for b in seq:
         with torch.no_grad():
             ref = o.forward_inference(b)
         pred = m.forward_inference(b)
         for k in ('pred_wp', 'mu_branches', 'pred_speed'):
             assert rel(pred[k], ref[k]) < 5e-4, (k, b['points'].shape)
+        if first is None:
+            first = (pred, {k: pred[k].clone() for k in ('pred_wp', 'mu_branches', 'pred_speed')})
+    # a pred the caller still holds is not overwritten by later forwards (the reference returns fresh tensors)
+    for k, v in first[1].items():
+        assert torch.equal(first[0][k], v), k
     # the staged cloud is padded to the bucket with points the voxeliser drops
     pb = m.eng.static('in.points')
     assert pb.shape[1] % 8192 == 0 and float(pb[0, -1, 0]) > 1e29

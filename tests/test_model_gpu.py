@@ -55,12 +55,13 @@ def compare_all(oracle, model, batch, tol=TOL):
     print({k: f'{v:.1e}' for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, bad
+    assert model.f16s_saturations() == 0
     return errs
 
 
-@pytest.mark.parametrize('impl', [1, 3])
+@pytest.mark.parametrize('impl', [1, 3, 4])
 def test_plumbing_config_b1_matches_oracle(impl):
-    """impl 1: every contraction on the SIMT fp32 kernel; impl 3: dense convs on tcgen05 3xTF32."""
+    """impl 1: every contraction on the SIMT fp32 kernel; impl 3: dense convs on tcgen05 3xTF32; impl 4: on tcgen05 scaled-split fp16."""
     from thinktwice_b200.config import PLUMBING_CONFIG
     _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000, impl=impl)
     compare_all(oracle, model, batch)
@@ -69,7 +70,7 @@ def test_plumbing_config_b1_matches_oracle(impl):
 def test_plumbing_config_b2_keeps_batch_coupled_look_semantics():
     """fact 4 of SURVEY.md: max_len over the batch, first B rows zeroed, divide by B — same on both sides."""
     from thinktwice_b200.config import PLUMBING_CONFIG
-    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 2, 1500, seed=1)
+    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 2, 1500, seed=1, impl=0)
     compare_all(oracle, model, batch)
 
 
@@ -85,7 +86,7 @@ def test_repeat_forward_is_bitwise_stable_where_deterministic():
 def test_decoder_depth_sweep_matches_oracle(K):
     """BASELINE.json configs[4] (K in {1,2,3,5,10}): K=1 and K=5 are the plumbing / full configs, here K=2,3,10."""
     from thinktwice_b200.config import PLUMBING_CONFIG
-    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 1000, seed=3, impl=3, refine_num=K)
+    _, oracle, model, batch = build_pair(PLUMBING_CONFIG, 1, 1000, seed=3, impl=0, refine_num=K)
     errs = compare_all(oracle, model, batch)
     assert oracle.decoder.config['refine_num'] == K and len(model.decoder.layers) == K
 
@@ -93,7 +94,7 @@ def test_decoder_depth_sweep_matches_oracle(K):
 def test_cuda_graph_replay_equals_eager():
     from thinktwice_b200.config import PLUMBING_CONFIG
     from thinktwice_b200.synthetic import make_batch
-    cfg, _, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000, impl=3)
+    cfg, _, model, batch = build_pair(PLUMBING_CONFIG, 1, 2000, impl=0)
     eager = {k: model.forward_inference(batch)[k].clone() for k in ('pred_wp', 'mu_branches', 'refine_BEV_feature')}
     model.enable_cuda_graph()
     for _ in range(2):                                              # capture, then a pure replay
@@ -110,7 +111,7 @@ def test_cuda_graph_replay_equals_eager():
 def full():
     """the thinktwice.py model pair (oracle + product, tensor-core engine), built once for the full-shape tests."""
     from thinktwice_b200.config import DEFAULT_CONFIG
-    cfg, oracle, model, batch = build_pair(DEFAULT_CONFIG, 1, 40000, impl=3)
+    cfg, oracle, model, batch = build_pair(DEFAULT_CONFIG, 1, 40000, impl=0)   # 0 = the product's default engine
     return dict(cfg=cfg, oracle=oracle, model=model, batch=batch)
 
 

@@ -94,7 +94,7 @@ class EncoderDecoder(nn.Module):
         dev = torch.device(device)
         lib.require_cuda(dev)
         if impl == lib.IMPL_AUTO:
-            impl = lib.IMPL_3XTF32                                  # default engine: tcgen05 3xTF32 (fp32-class)
+            impl = lib.IMPL_F16S                                    # default engine: tcgen05 on scaled-split fp16 operands (fp32-class)
         self.eng = e = Engine(dev, impl)
         pk = Packer(self.state_dict(), dev, tc_mode=impl if impl in (lib.IMPL_TF32, lib.IMPL_3XTF32, lib.IMPL_F16S) else 0)
         self.img_encoder.prepare(pk, e)
@@ -203,6 +203,14 @@ class EncoderDecoder(nn.Module):
         self.last_cam_feat = cam                                   # cam['seg'] etc. for parity checks
         return pred
 
+    def f16s_saturations(self, reset=True):
+        """values the scaled-split fp16 engine had to clamp to +-65504 since the last reset (0 in a healthy network; the fp32
+        outputs stay exact, only tensor-core OPERANDS saturate).  Synchronises the current stream: call it between forwards."""
+        import ctypes
+        n = ctypes.c_uint(0)
+        lib.check(lib.load().tt_f16s_saturation_count(ctypes.byref(n), int(reset), lib._stream()), 'tt_f16s_saturation_count')
+        return int(n.value)
+
     def enable_cuda_graph(self, flag=True):
         """Replay the device half as one CUDA graph (no per-kernel host launch cost).  The graph is captured on
         the first forward after this call (after one eager warm-up that allocates every buffer)."""
@@ -217,7 +225,7 @@ class EncoderDecoder(nn.Module):
         self.epoch = 10000
         key = self.stage(batch)
         if not getattr(self, 'use_graph', False):
-            return self._device_forward()
+            return self._own(self._device_forward())
         g = self._graphs.get(key)
         if g is None:
             self._device_forward()                                 # eager warm-up: allocates all persistent buffers
@@ -227,7 +235,18 @@ class EncoderDecoder(nn.Module):
                 pred = self._device_forward()
             g = self._graphs[key] = (graph, pred)
         g[0].replay()
-        return g[1].fresh()
+        return self._own(g[1].fresh())
+
+    SMALL_OUTPUTS = ('pred_speed', 'pred_value_traj', 'pred_features_traj', 'pred_value_ctrl', 'pred_features_ctrl', 'pred_wp',
+                     'mu_branches', 'sigma_branches', 'future_mu', 'future_sigma')
+
+    def _own(self, pred):
+        """The forward writes into persistent arena buffers (static addresses: graph-replayable).  The small outputs — what the
+        agent keeps and post-processes (thinktwice_agent.py:459-461) — are handed out as fresh tensors like the reference does;
+        the bulky feature stacks (refine_*_BEV_feature, bev_feature) stay lazy views of the arena: clone them to keep them."""
+        for k in self.SMALL_OUTPUTS:
+            pred[k] = pred[k].clone()
+        return pred
 
     def forward(self, is_eval=True, return_loss=False, **kwargs):
         """Reference signature (framework:393-407: `forward(is_eval=True, **kwargs)` with the batch as keywords).

@@ -37,16 +37,22 @@ def main():
     L = lib.load()
     for name, N, H, W, Cin, Cout, k, stride, pad, use_res in SHAPES:
         g = torch.Generator().manual_seed(0)
-        x = FMap(torch.randn(N, H, W, Cin, generator=g).cuda(), N, H, W, Cin)
+        N = N * int(os.environ.get('NMUL', '1'))
+        xt = torch.randn(N, H, W, Cin, generator=g).cuda()
         w = torch.randn(Cout, Cin, k, k, generator=g) * 0.05
         OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         res = FMap(torch.randn(N, OH, OW, Cout, generator=g).cuda(), N, OH, OW, Cout) if use_res else None
         gf = 2.0 * N * OH * OW * Cin * k * k * Cout / 1e9
         mb = (N * H * W * Cin + N * OH * OW * Cout * (2 if use_res else 1)) * 4 / 1e6
         line = f'{name:36s} {gf:7.1f} GF {mb:6.0f} MB(min)'
-        for impl, tag in [(int(i), {1: 'simt', 2: 'tf32', 3: '3xtf32'}[int(i)]) for i in os.environ.get('IMPLS', '1,2,3').split(',')]:
+        for impl, tag in [(int(i), {1: 'simt', 2: 'tf32', 3: '3xtf32', 4: 'f16s'}[int(i)]) for i in os.environ.get('IMPLS', '1,3,4').split(',')]:
             eng = Engine('cuda:0', impl=impl); eng.tc_min_rows = 1
             pw = Packer({'c.weight': w}, torch.device('cuda:0'), tc_mode=impl if impl > 1 else 0).conv('c')
+            x = FMap(xt, N, H, W, Cin)
+            if impl == 4:                                              # input with a split companion, as a producing conv would leave it
+                x = eng.fmap('b.x', N, H, W, Cin, split=True)
+                x.t.copy_(xt)
+                eng.sync_split(x)
             for dbg in (dbg_list if impl > 1 else [0]):
                 L.tt_debug_set(dbg)
                 us = run(eng, x, pw, res, k, stride, pad)
