@@ -133,14 +133,25 @@ int tt_conv2d(const tt_conv_desc* d, const float* x, const float* w, const float
  * consumer's TMA loads are tensor-core ready; tt_split_f16 converts fp32 rows produced by other kernels.
  *   w_split: [2][Cout][taps][Cin8] halves, Cin8 = Cin rounded up to 8 (zero padded), plane 0 = hi, plane 1 = lo'.
  *   products: hi*hi + (hi*lo' + lo'*hi) / 2048, fp32 accumulation drained into registers every 128 K elements.
- *   y (fp32) and y_split are both optional outputs (at least one); res / res2 / bias are fp32 as in tt_conv2d.
+ *   y (fp32) and y_split are both optional outputs (at least one) — a tensor only convolutions read needs no fp32 copy;
+ *   each residual is given EITHER as fp32 (res / res2) or as split planes (res_split / res2_split, same element offsets).
  * Needs groups 1, stride 1|2, x_ld % 8 == 0 (halves), y_ld % 4 == 0, 16-byte aligned pointers, else TT_ERR_UNSUPPORTED.
  */
-int tt_conv2d_f16s(const tt_conv_desc* d, const void* x_split, long long x_plane, const void* w_split, const float* bias,
-                   const float* res, const float* res2, float* y, void* y_split, long long y_plane, tt_stream_t stream);
+typedef struct {
+  const void* x_split; long long x_plane;     /* input: hi plane pointer (at the channel offset), halves to the lo' plane */
+  const void* w_split;                        /* [2][Cout][taps][Cin8] */
+  const float* bias;                          /* fp32 [Cout] (or table, bias_n_mod) or NULL */
+  const float* res;  const void* res_split;  long long res_plane;
+  const float* res2; const void* res2_split; long long res2_plane;
+  float* y; void* y_split; long long y_plane; /* outputs */
+} tt_f16s_io;
+int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stream);
 /* fp32 rows [rows][x_ld] (first `cols` columns) -> split planes [2][rows][y_ld]; only the first *row_count rows when given */
 int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plane, long long y_ld, long long rows, int cols,
                  const int* row_count, tt_stream_t stream);
+/* split planes -> fp32 rows (hi + lo' / 2048): for a non-convolution kernel that must read a tensor stored as planes only */
+int tt_merge_f16(const void* x_split, long long x_plane, long long x_ld, float* y, long long y_ld, long long rows, int cols,
+                 tt_stream_t stream);
 /* epilogue threads that had to clamp a value to +-65504 since the last reset (host int; synchronises `stream`) */
 int tt_f16s_saturation_count(unsigned int* out_host, int reset, tt_stream_t stream);
 

@@ -37,6 +37,8 @@ def emulated(monkeypatch):
     monkeypatch.setattr(lib, 'require_cuda', lambda dev: None)
     monkeypatch.setattr(lib, '_p', p)
     monkeypatch.setattr(lib, '_stream', lambda: None)
+    monkeypatch.setattr(lib, 'F16sIO', emu_lib.IO)
+    monkeypatch.setattr(lib, 'ref', lambda s: s)
     import thinktwice_b200.engine as engine
     import thinktwice_b200.lss as lss
     import thinktwice_b200.lidarnet as lidarnet

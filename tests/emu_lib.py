@@ -27,6 +27,14 @@ class Ptr:
 
 
 NULL = Ptr(None)
+
+
+class IO:
+    """stand-in for lib.F16sIO (tt_f16s_io): same field names, Ptr objects instead of addresses."""
+
+    def __init__(self):
+        self.x_split = self.w_split = self.bias = self.res = self.res_split = self.res2 = self.res2_split = self.y = self.y_split = NULL
+        self.x_plane = self.res_plane = self.res2_plane = self.y_plane = 0
 _by_addr = {}
 
 
@@ -114,7 +122,7 @@ class Emu:
                 return _pix_view(x, d.N, d.H, d.W if C_ == d.Cin else d.x_hstride // d.x_ld, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
             Wv = d.W if C_ == d.Cin else d.x_hstride // d.x_ld
             hi = _pix_view(x, d.N, d.H, Wv, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
-            lo = _pix_view(Ptr(x.t, x.off + f16s['x_plane']), d.N, d.H, Wv, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
+            lo = _pix_view(Ptr(x.t, x.off + f16s.x_plane), d.N, d.H, Wv, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
             return hi + lo / 2048.0
         xin = xview(d.Cin).permute(0, 3, 1, 2) if d.x_ld >= d.Cin else None
         if f16s is not None:                                           # [2][Cout][taps][Cin8] scaled-split half planes
@@ -144,32 +152,41 @@ class Emu:
                 out = out + tab[torch.arange(d.N) % d.bias_n_mod][:, None, None, :]
             else:
                 out = out + bias.flat()[:d.Cout].double()
+        def resview(p32, psplit, plane, N_, H_, W_, ld_, coff_):
+            if p32:
+                return _pix_view(p32, N_, H_, W_, ld_, C=d.Cout + coff_)[..., coff_:].double()
+            hi = _pix_view(psplit, N_, H_, W_, ld_, C=d.Cout + coff_)[..., coff_:].double()
+            lo = _pix_view(Ptr(psplit.t, psplit.off + plane), N_, H_, W_, ld_, C=d.Cout + coff_)[..., coff_:].double()
+            return hi + lo / 2048.0
+        rs_, rp_ = (f16s.res_split, f16s.res_plane) if f16s is not None else (NULL, 0)
+        r2s_, r2p_ = (f16s.res2_split, f16s.res2_plane) if f16s is not None else (NULL, 0)
         if d.res_mode == 1:
-            out = out + _pix_view(res, d.N, d.OH, d.OW, d.res_ld, C=d.Cout + d.res_coff)[..., d.res_coff:].double()
+            out = out + resview(res, rs_, rp_, d.N, d.OH, d.OW, d.res_ld, d.res_coff)
         elif d.res_mode == 2:                                          # nearest-upsampled residual (PAFPN top-down)
-            r = _pix_view(res, d.N, d.res_H, d.res_W, d.res_ld, C=d.Cout + d.res_coff)[..., d.res_coff:].double()
+            r = resview(res, rs_, rp_, d.N, d.res_H, d.res_W, d.res_ld, d.res_coff)
             ih = (torch.arange(d.OH) * d.res_H) // d.OH
             iw = (torch.arange(d.OW) * d.res_W) // d.OW
             out = out + r[:, ih][:, :, iw]
-        if res2:
-            out = out + _pix_view(res2, d.N, d.OH, d.OW, d.res2_ld, C=d.Cout + d.res2_coff)[..., d.res2_coff:].double()
+        if res2 or r2s_:
+            out = out + resview(res2, r2s_, r2p_, d.N, d.OH, d.OW, d.res2_ld, d.res2_coff)
         out = _act(out, d.act).float()
         if y:
             yv = _pix_view(y, d.N, d.yH, d.yW, d.y_ld, d.y_nstride, 0, d.Cout + d.y_coff)[..., d.y_coff:]
             yv[:, d.oy_add::d.oy_mul, d.ox_add::d.ox_mul][:, :d.OH, :d.OW] = out
-        if f16s is not None and f16s['y_split']:
+        if f16s is not None and f16s.y_split:
             hi, lo = _split_f16(out)
-            for plane, val in ((0, hi), (f16s['y_plane'], lo)):
-                pv = Ptr(f16s['y_split'].t, f16s['y_split'].off + plane)
+            for plane, val in ((0, hi), (f16s.y_plane, lo)):
+                pv = Ptr(f16s.y_split.t, f16s.y_split.off + plane)
                 yv = _pix_view(pv, d.N, d.yH, d.yW, d.y_ld, d.y_nstride, 0, d.Cout + d.y_coff)[..., d.y_coff:]
                 yv[:, d.oy_add::d.oy_mul, d.ox_add::d.ox_mul][:, :d.OH, :d.OW] = val
         return 0
 
-    def tt_conv2d_f16s(self, d, x_split, x_plane, w_split, bias, res, res2, y, y_split, y_plane, stream):
-        """include/tt_b200.h (2b): operands are read from the split planes (x = hi + lo' / 2048), outputs written as fp32 and / or split."""
-        assert x_split.t.dtype == torch.float16 and w_split.t.dtype == torch.float16
-        return self.tt_conv2d(d, x_split, w_split, bias, res, res2, NULL, NULL, y, NULL, stream,
-                              f16s=dict(x_plane=_v(x_plane), y_split=y_split, y_plane=_v(y_plane)))
+    def tt_conv2d_f16s(self, d, io, stream):
+        """include/tt_b200.h (2b): operands are read from the split planes (x = hi + lo' / 2048), residuals from fp32 or split
+        planes, outputs written as fp32 and / or split."""
+        assert io.x_split.t.dtype == torch.float16 and io.w_split.t.dtype == torch.float16
+        assert io.y or io.y_split
+        return self.tt_conv2d(d, io.x_split, io.w_split, io.bias, io.res, io.res2, NULL, NULL, io.y, NULL, stream, f16s=io)
 
     def tt_split_f16(self, x, x_ld, y_split, y_plane, y_ld, rows, cols, row_count, stream):
         self.launches += 1
@@ -179,6 +196,14 @@ class Emu:
         hi, lo = _split_f16(src)
         torch.as_strided(y_split.flat(), (n, cols), (y_ld, 1)).copy_(hi)
         torch.as_strided(Ptr(y_split.t, y_split.off + y_plane).flat(), (n, cols), (y_ld, 1)).copy_(lo)
+        return 0
+
+    def tt_merge_f16(self, x_split, x_plane, x_ld, y, y_ld, rows, cols, stream):
+        self.launches += 1
+        x_plane, x_ld, y_ld, rows = _v(x_plane), _v(x_ld), _v(y_ld), _v(rows)
+        hi = torch.as_strided(x_split.flat(), (rows, cols), (x_ld, 1)).float()
+        lo = torch.as_strided(Ptr(x_split.t, x_split.off + x_plane).flat(), (rows, cols), (x_ld, 1)).float()
+        torch.as_strided(y.flat(), (rows, cols), (y_ld, 1)).copy_(hi + lo / 2048.0)
         return 0
 
     def tt_f16s_saturation_count(self, out_host, reset, stream):
@@ -411,6 +436,10 @@ class Emu:
 
     def tt_copy2d(self, src, src_ld, dst, dst_ld, rows, cols, rdiv, rmod, stream):
         self.launches += 1
+        if src.t.dtype == torch.float16:                            # the C ABI moves 4-byte words: a pair of halves is one word
+            assert dst.t.dtype == torch.float16 and src.off % 2 == 0 and dst.off % 2 == 0
+            src = Ptr(src.t.reshape(-1).view(torch.float32), src.off // 2)
+            dst = Ptr(dst.t.reshape(-1).view(torch.float32), dst.off // 2)
         r = (torch.arange(rows) // rdiv) % rmod
         n_src = int(r.max()) + 1
         sv = torch.as_strided(src.flat(), (n_src, cols), (src_ld, 1))

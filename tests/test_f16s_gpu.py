@@ -256,3 +256,46 @@ def test_f16s_sparse_conv_layers_match_oracle(Cin, Cout, density):
         assert relerr(got, ref) < 1e-5
         val = out_s[0].view(cap_out, Cout)[:m].double() + out_s[1].view(cap_out, Cout)[:m].double() / 2048.0
         assert relerr(val, out[:m]) < 6e-7
+
+
+def test_f16s_split_only_tensors_chain_through_convs_residuals_and_copies():
+    """fmt='s': a tensor only convolutions read is stored as split planes alone — operands AND residuals come from the planes
+    (tt_f16s_io.res_split), under-filled layers still split-K through a lent fp32 workspace, concat copies move planes, and
+    tt_merge_f16 rebuilds fp32 where a map keeps both forms."""
+    from thinktwice_b200.weights import Packer
+    gen = torch.Generator().manual_seed(9)
+    eng = engine()
+    eng.tc_min_rows = 128
+    N, H, W = 2, 24, 32
+    x = torch.randn(N, 64, H, W, generator=gen)
+    w1 = torch.randn(64, 64, 3, 3, generator=gen) * 0.05
+    w2 = torch.randn(64, 64, 1, 1, generator=gen) * 0.12
+    w3 = torch.randn(128, 64, 3, 3, generator=gen) * 0.04
+    dev = torch.device('cuda:0')
+    p1, p2, p3 = (Packer({'c.weight': w}, dev, tc_mode=IMPL).conv('c') for w in (w1, w2, w3))
+    xf = to_fmap_s(eng, 'so.x', x.cuda())
+    y1 = eng.conv(xf, p1, name='so.y1', pad=1, act=1, fmt='s')
+    assert y1.t is None and y1.s is not None
+    y2 = eng.conv(y1, p2, name='so.y2', act=1, res=y1, fmt='s')             # split operand, split residual, split-only output
+    cat = eng.fmap('so.cat', N, H, W, 128, fmt='fs')
+    eng.copy_cols(y2, cat.slice(0, 64))                                       # planes -> planes (+ fp32 rebuilt by tt_merge_f16)
+    eng.copy_cols(y1, cat.slice(64, 64))
+    y3 = eng.conv(cat, p3, name='so.y3', stride=2, pad=1, res2=None, fmt='s')
+    torch.cuda.synchronize()
+    r1 = F.relu(F.conv2d(x.double(), w1.double(), padding=1))
+    r2 = F.relu(F.conv2d(r1, w2.double()) + r1)
+    r3 = F.conv2d(torch.cat([r2, r1], 1), w3.double(), stride=2, padding=1)
+    assert relerr(y1.nchw(), r1) < TOL and relerr(y2.nchw(), r2) < TOL
+    assert relerr(cat.nchw(), torch.cat([r2, r1], 1)) < TOL                   # the fp32 side of the concat buffer
+    assert relerr(split_value(cat), torch.cat([r2, r1], 1)) < TOL
+    assert y3.t is None and relerr(y3.nchw(), r3) < 2 * TOL
+    assert eng.stats['late_split'] == 0
+    # an fp32 kernel asked to read a split-only map fails loudly
+    from thinktwice_b200 import lib
+    with pytest.raises(lib.TTError):
+        eng.maxpool3x3s2(y1, 'so.pool')
+    # a non-conv producer with a split-only result: fp32 lives in the lane scratch only until it is converted
+    up = eng.upsample2x(cat.slice(0, 128), 'so.up', fmt='s')
+    assert up.t is None
+    ref_up = F.interpolate(torch.cat([r2, r1], 1), scale_factor=2, mode='bilinear', align_corners=True)
+    assert relerr(up.nchw(), ref_up) < TOL

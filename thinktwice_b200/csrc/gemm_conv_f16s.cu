@@ -85,11 +85,23 @@ TT_DEVICE void split4(const float4& o, uint2& hi, uint2& lo, bool& sat) {
   lo.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
 }
 
+TT_DEVICE float4 load_split4(const __half* hi_ptr, long long plane) {
+  const uint2 h = *reinterpret_cast<const uint2*>(hi_ptr);
+  const uint2 l = *reinterpret_cast<const uint2*>(hi_ptr + plane);
+  const __half2 h0 = *reinterpret_cast<const __half2*>(&h.x), h1 = *reinterpret_cast<const __half2*>(&h.y);
+  const __half2 l0 = *reinterpret_cast<const __half2*>(&l.x), l1 = *reinterpret_cast<const __half2*>(&l.y);
+  const float2 a = __half22float2(h0), b = __half22float2(h1), c = __half22float2(l0), e = __half22float2(l1);
+  return make_float4(fmaf(c.x, LO_INV, a.x), fmaf(c.y, LO_INV, a.y), fmaf(e.x, LO_INV, b.x), fmaf(e.y, LO_INV, b.y));
+}
+
 struct HArgs {
   tt_conv_desc d;
   const float* bias;
   const float* res;
   const float* res2;
+  const __half* res_s;   // residuals given as split planes instead of fp32 (same element offsets; lo' plane res*_plane further)
+  const __half* res2_s;
+  long long res_plane, res2_plane;
   float* y;              // fp32 output (may be NULL when only the split planes are wanted)
   __half* ys;            // split output: hi plane at the same element offsets as y; lo' plane ys_plane halves further (or NULL)
   long long ys_plane;
@@ -367,10 +379,22 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (p.res) {
 #pragma unroll
             for (int j = 0; j < HN; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + r1 + n0 + j));
+          } else if (p.res_s) {
+#pragma unroll
+            for (int j = 0; j < HN; j += 64) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_s + r1 + n0 + j));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_s + p.res_plane + r1 + n0 + j));
+            }
           }
           if (p.res2) {
 #pragma unroll
             for (int j = 0; j < HN; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res2 + r2 + n0 + j));
+          } else if (p.res2_s) {
+#pragma unroll
+            for (int j = 0; j < HN; j += 64) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res2_s + r2 + n0 + j));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res2_s + p.res2_plane + r2 + n0 + j));
+            }
           }
         }
       }
@@ -419,7 +443,9 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             rb[i] = ra[i];
             if (fl[i] & 1) {
               if (p.res) ra[i] = *reinterpret_cast<const float4*>(p.res + row_r1[rr] + col);
+              else if (p.res_s) ra[i] = load_split4(p.res_s + row_r1[rr] + col, p.res_plane);
               if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + row_r2[rr] + col);
+              else if (p.res2_s) rb[i] = load_split4(p.res2_s + row_r2[rr] + col, p.res2_plane);
             }
           }
 #pragma unroll
@@ -461,7 +487,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // split-K / sparse companions.  init: y = bias + res + res2 before the tensor-core kernel red.adds its partial sums;
 // finish: y = act(y) and, when asked, the split planes of the finished rows.
 __global__ void f16s_splitk_init_kernel(const tt_conv_desc d, const float* __restrict__ bias, const float* __restrict__ res,
-                                        const float* __restrict__ res2, float* __restrict__ y) {
+                                        const float* __restrict__ res2, const __half* __restrict__ res_s, long long res_plane,
+                                        const __half* __restrict__ res2_s, long long res2_plane, float* __restrict__ y) {
   const int HWo = d.OH * d.OW, C4 = d.Cout / 4;
   const long long total = (long long)d.N * HWo * C4;
   const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
@@ -472,6 +499,8 @@ __global__ void f16s_splitk_init_kernel(const tt_conv_desc d, const float* __res
     float4 v = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (res) { const float4 t = *reinterpret_cast<const float4*>(res + pix * d.res_ld + d.res_coff + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
     if (res2) { const float4 t = *reinterpret_cast<const float4*>(res2 + pix * d.res2_ld + d.res2_coff + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    if (res_s) { const float4 t = load_split4(res_s + pix * d.res_ld + d.res_coff + c, res_plane); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    if (res2_s) { const float4 t = load_split4(res2_s + pix * d.res2_ld + d.res2_coff + c, res2_plane); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
     *reinterpret_cast<float4*>(y + n * yns + (pix - (long long)n * HWo) * d.y_ld + d.y_coff + c) = v;
   }
 }
@@ -512,7 +541,19 @@ __global__ void split_rows_kernel(const float* __restrict__ x, long long x_ld, _
     *reinterpret_cast<uint2*>(ys + r * ys_ld + c) = hi;
     *reinterpret_cast<uint2*>(ys + ys_plane + r * ys_ld + c) = lo;
   }
-  if (sat) atomicAdd(&g_f16s_saturated, 1u);
+  // not counted in g_f16s_saturated: this converter also sweeps arena regions no kernel has written yet (whole-buffer refreshes),
+  // whose bit patterns are arbitrary; values that matter were produced — and counted — by a convolution epilogue
+}
+
+// split planes -> fp32 rows (a non-convolution kernel needs the fp32 value of a tensor that is stored as planes only)
+__global__ void merge_rows_kernel(const __half* __restrict__ xs, long long xs_plane, long long xs_ld, float* __restrict__ y, long long y_ld,
+                                  long long rows, int cols4) {
+  const long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    *reinterpret_cast<float4*>(y + r * y_ld + c) = load_split4(xs + r * xs_ld + c, xs_plane);
+  }
 }
 
 // sparse rows: y = act(y + res) for the first *count rows, plus their split planes
@@ -608,18 +649,38 @@ int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plan
   return TT_OK;
 }
 
-int tt_conv2d_f16s(const tt_conv_desc* d, const void* x_split, long long x_plane, const void* w_split, const float* bias,
-                   const float* res, const float* res2, float* y, void* y_split, long long y_plane, tt_stream_t stream) {
-  TT_REQUIRE(d && x_split && w_split && (y || y_split), "tt_conv2d_f16s", "null argument");
-  TT_REQUIRE(d->res_mode == TT_RES_NONE || res != nullptr, "tt_conv2d_f16s", "res_mode set without a residual");
+int tt_merge_f16(const void* x_split, long long x_plane, long long x_ld, float* y, long long y_ld, long long rows, int cols,
+                 tt_stream_t stream) {
+  TT_REQUIRE(x_split && y && rows >= 0 && cols > 0, "tt_merge_f16", "bad argument");
+  TT_REQUIRE(cols % 4 == 0 && x_ld % 4 == 0 && y_ld % 4 == 0 && x_plane % 4 == 0 && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(x_split) & 7) == 0),
+             "tt_merge_f16", "needs 4-element alignment");
+  if (rows == 0) return TT_OK;
+  const long long total = rows * (cols / 4);
+  const int nb = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  merge_rows_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(x_split), x_plane, x_ld, y, y_ld, rows, cols / 4);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_merge_f16");
+  return TT_OK;
+}
+
+int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stream) {
+  TT_REQUIRE(d && io && io->x_split && io->w_split && (io->y || io->y_split), "tt_conv2d_f16s", "null argument");
+  const void* x_split = io->x_split; const long long x_plane = io->x_plane;
+  const void* w_split = io->w_split; const float* bias = io->bias;
+  const float* res = io->res; const float* res2 = io->res2;
+  float* y = io->y; void* y_split = io->y_split; const long long y_plane = io->y_plane;
+  TT_REQUIRE(d->res_mode == TT_RES_NONE || res != nullptr || io->res_split != nullptr, "tt_conv2d_f16s", "res_mode set without a residual");
+  TT_REQUIRE(!(res && io->res_split) && !(res2 && io->res2_split), "tt_conv2d_f16s", "a residual is given either as fp32 or as split planes");
   const long long xhs = d->x_hstride ? d->x_hstride : (long long)d->W * d->x_ld;
   const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * xhs;
   const bool ok = d->groups == 1 && (d->stride == 1 || d->stride == 2) && d->Cout % 4 == 0 && d->x_ld % 8 == 0 && xhs % 8 == 0 &&
                   xns % 8 == 0 && x_plane % 8 == 0 && d->y_ld % 4 == 0 && d->y_coff % 4 == 0 && d->y_nstride % 4 == 0 && y_plane % 4 == 0 &&
-                  (d->res_mode == TT_RES_NONE || d->res_ld % 4 == 0) && d->res2_ld % 4 == 0 &&
+                  (d->res_mode == TT_RES_NONE || (d->res_ld % 4 == 0 && d->res_coff % 4 == 0)) && d->res2_ld % 4 == 0 && d->res2_coff % 4 == 0 &&
+                  io->res_plane % 4 == 0 && io->res2_plane % 4 == 0 &&
                   ((reinterpret_cast<uintptr_t>(x_split) | reinterpret_cast<uintptr_t>(w_split) | reinterpret_cast<uintptr_t>(y) |
                     reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(res2) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(y_split) & 7) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(y_split) | reinterpret_cast<uintptr_t>(io->res_split) | reinterpret_cast<uintptr_t>(io->res2_split)) & 7) == 0 &&
                   d->OH == (d->H + 2 * d->pad - d->dil * (d->KH - 1) - 1) / d->stride + 1 &&
                   d->OW == (d->W + 2 * d->pad - d->dil * (d->KW - 1) - 1) / d->stride + 1;
   if (!ok) {
@@ -633,6 +694,8 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const void* x_split, long long x_plane
   memset(&a, 0, sizeof(a));
   a.d = *d;
   a.bias = bias; a.res = res; a.res2 = res2; a.y = y;
+  a.res_s = static_cast<const __half*>(io->res_split); a.res_plane = io->res_plane;
+  a.res2_s = static_cast<const __half*>(io->res2_split); a.res2_plane = io->res2_plane;
   a.ys = static_cast<__half*>(y_split); a.ys_plane = y_plane;
   a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;   // 2 stages = K 128 = 8 truncating accumulations per chunk
   a.n_slabs = (d->Cin + KE - 1) / KE;
@@ -691,10 +754,11 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const void* x_split, long long x_plane
   const long long total4 = (long long)d->N * d->OH * d->OW * (d->Cout / 4);
   const int nb_ew = (int)((total4 + 255) / 256 > 1184 ? 1184 : (total4 + 255) / 256);
   if (a.splits > 1) {
-    f16s_splitk_init_kernel<<<nb_ew, 256, 0, st>>>(*d, bias, d->res_mode != TT_RES_NONE ? res : nullptr, res2, y);
+    f16s_splitk_init_kernel<<<nb_ew, 256, 0, st>>>(*d, bias, d->res_mode != TT_RES_NONE ? res : nullptr, res2,
+                                                   d->res_mode != TT_RES_NONE ? a.res_s : nullptr, a.res_plane, a.res2_s, a.res2_plane, y);
     ++g_tt_launches;
     TT_CHECK_LAUNCH("tt_conv2d_f16s(split-k init)");
-    a.bias = nullptr; a.res = nullptr; a.res2 = nullptr;
+    a.bias = nullptr; a.res = nullptr; a.res2 = nullptr; a.res_s = nullptr; a.res2_s = nullptr;
     a.d.act = TT_ACT_NONE;
     a.d.res_mode = TT_RES_NONE;
   }

@@ -5,6 +5,7 @@ Buffers are allocated once per (name, shape) and reused on every forward, so a s
 performs no allocation (CUDA-graph capturable) and keeps activations resident in HBM.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -41,11 +42,23 @@ class FMap:
 
     def dense(self):
         """contiguous (N, H, W, C) torch view/copy of the logical tensor (debug / tests / outputs)."""
+        if self.t is None:                                         # split-only tensor: hi + lo' / 2048 (debug / test path)
+            n = self.N * self.H * self.W * self.ld
+            hi, lo = self.s[0].view(-1)[:n], self.s[1].view(-1)[:n]
+            full = (hi.float() + lo.float() / 2048.0).view(self.N, self.H, self.W, self.ld)
+            return full[..., self.coff:self.coff + self.C]
         v = self.t.view(self.N, self.H, self.W, self.ld)[..., self.coff:self.coff + self.C]
         return v
 
     def nchw(self):
         return self.dense().permute(0, 3, 1, 2)
+
+
+def _t(fm):
+    """the fp32 tensor of a map, or a loud error when the map is stored as split planes only."""
+    if fm.t is None:
+        raise lib.TTError('this kernel reads / writes fp32 but the map is stored as split planes only (fmt="s")')
+    return fm.t
 
 
 def _ps(fm):
@@ -110,6 +123,7 @@ class Engine:
         self.cur = {}                 # name -> the buffer the latest upload(name, ...) went to (shape-keyed arena: see static())
         self.conv_ws = {}             # per lane: grow-only conv workspace (split-K partial sums of the SIMT kernel)
         self._ws_retired = []         # outgrown workspaces stay alive: CUDA graphs captured earlier still point at them
+        self._scratch, self._tmp_maps = {}, set()
         self.lane = 0               # 0 = main stream; 1 = side stream (independent branch running concurrently)
         self._side = None
         self.overlap = True         # run independent branches (side_branch) concurrently
@@ -118,6 +132,8 @@ class Engine:
         self.tc_strides = (1, 2)
         self.split = impl == lib.IMPL_F16S   # feature maps carry a scaled-split fp16 companion (gemm_conv_f16s.cu)
         self.stats = {'late_split': 0}
+        self._cur_name = None
+        self.force_fs = set(filter(None, os.environ.get('TT_FORCE_FS', '').split(',')))   # debugging: maps kept in both formats
         self.prof = None            # bench.py: list of (name, flops, start_event, end_event) per conv launch
         lib.load()
 
@@ -164,13 +180,59 @@ class Engine:
         except KeyError:
             raise KeyError(f'static buffer {name} has not been staged') from None
 
-    def fmap(self, name, N, H, W, C, ld=None, zero=False, split=None):
+    def fmap(self, name, N, H, W, C, ld=None, zero=False, split=None, fmt=None):
+        """feature-map buffer `name`.  fmt (scaled-split engine only): 'fs' fp32 + split companion (default), 'f' fp32 only (nobody
+        feeds it to a tensor-core conv), 's' split planes only (ONLY convolutions read it: operands and residuals come from the
+        companion, no fp32 copy is stored).  's' is honoured when the map can feed the tensor-core kernel at all (row pitch a
+        multiple of 8 halves, >= tc_min_rows rows); otherwise it degrades to 'f' and consumers convert late."""
         ld = ld if ld is not None else C
-        t = self.buf(name, (N, H, W, ld), zero=zero)
-        want = self.split if split is None else (split and self.split)
+        if split is not None:
+            fmt = 'fs' if split else 'f'
+        if not self.split:
+            fmt = 'f'
+        elif fmt is None or name in self.force_fs or '*' in self.force_fs:
+            fmt = 'fs'
+        rows = N * H * W
+        if fmt == 's' and not (ld % 8 == 0 and ld >= 32 and rows >= self.tc_min_rows):
+            fmt = 'f'
         # a tensor-core conv needs >= 128 GEMM rows: smaller maps only ever feed the SIMT kernels
-        sc = self.buf(name + '#s', (2, N * H * W * ld), torch.float16, zero=True) if want and ld % 4 == 0 and ld >= 32 and N * H * W >= 128 else None
+        if 's' in fmt and not (ld % 4 == 0 and ld >= 32 and rows >= 128):
+            fmt = 'f'
+        t = self.buf(name, (N, H, W, ld), zero=zero) if 'f' in fmt else None
+        sc = self.buf(name + '#s', (2, rows * ld), torch.float16, zero=True) if 's' in fmt else None
         return FMap(t, N, H, W, C, ld, 0, sc)
+
+    def scratch_f32(self, numel):
+        """per-lane fp32 scratch (grow-only; outgrown buffers stay alive for already captured graphs): the fp32 side of an
+        operation whose result is kept as split planes only."""
+        sb = self._scratch.get(self.lane)
+        if sb is None or sb.numel() < numel:
+            if sb is not None:
+                self._ws_retired.append(sb)
+            sb = self._scratch[self.lane] = torch.empty(int(numel), dtype=torch.float32, device=self.device)
+        return sb
+
+    def out_map(self, name, N, H, W, C, fmt=None, ld=None):
+        """output map of a NON-convolution kernel (they write fp32): for fmt 's' the fp32 side lives in the lane's scratch just long
+        enough to be converted (finish_out)."""
+        fm = self.fmap(name, N, H, W, C, ld, fmt=fmt)
+        if fm.t is None:
+            n = N * H * W * fm.ld
+            fm.t = self.scratch_f32(n)[:n].view(N, H, W, fm.ld)
+            self._tmp_maps.add(id(fm))
+        return fm
+
+    def finish_out(self, fm):
+        self.sync_split(fm)
+        if id(fm) in self._tmp_maps:
+            self._tmp_maps.discard(id(fm))
+            fm.t = None                                             # the scratch is free again: only the planes persist
+        return fm
+
+    def need_f32(self, fm, what):
+        if fm.t is None:
+            raise lib.TTError(f'{what}: the input map is stored as split planes only (fmt="s") but this kernel reads fp32')
+        return fm
 
     def wrap(self, t, C=None):
         """wrap an existing contiguous (N, H, W, ld) tensor."""
@@ -193,6 +255,14 @@ class Engine:
                  C.c_longlong(fm.rows()), w, None)
         return fm
 
+    def merge_split(self, fm):
+        """fp32 values of `fm` rebuilt from its split planes (hi + lo' / 2048), for maps that keep both representations."""
+        if (fm.C | fm.coff | fm.ld) % 4:
+            raise lib.TTError('merge_split: needs 4-column alignment')
+        lib.call('tt_merge_f16', _p(fm.s, fm.coff), C.c_longlong(fm.s.numel() // 2), C.c_longlong(fm.ld), _p(fm.t, fm.coff), C.c_longlong(fm.ld),
+                 C.c_longlong(fm.rows()), fm.C)
+        return fm
+
     def with_split(self, fm):
         """`fm` with a valid split companion: its own, or a late one (allocated per underlying buffer, converted now)."""
         if fm.s is not None:
@@ -202,18 +272,19 @@ class Engine:
         if sc is None:
             sc = self.bufs[key] = torch.zeros((2, fm.t.numel()), dtype=torch.float16, device=self.device)
         self.stats['late_split'] += 1
+        self.stats.setdefault('late_names', []).append(self._cur_name)
         return self.sync_split(FMap(fm.t, fm.N, fm.H, fm.W, fm.C, fm.ld, fm.coff, sc))
 
     # ------------------------------------------------------------------ conv / linear
     def conv(self, x, pw, out=None, name=None, stride=1, pad=0, dil=1, act=0, res=None, res_mode=0, res2=None,
-             scatter=None, out_ld=None, impl=None, x_nstride=0, y_nstride=0, n_images=None, bias_n_mod=0, x_hstride=0):
+             scatter=None, out_ld=None, impl=None, x_nstride=0, y_nstride=0, n_images=None, bias_n_mod=0, x_hstride=0, fmt=None):
         """y = act(conv(x) + bias + res + res2).  `out` (FMap) selects the destination (concat slice / scatter
         target); otherwise a buffer `name` is created.  scatter = (oy_mul, oy_add, ox_mul, ox_add)."""
         assert x.C == pw.Cin, (x.C, pw.Cin, name)
         OH = (x.H + 2 * pad - dil * (pw.KH - 1) - 1) // stride + 1
         OW = (x.W + 2 * pad - dil * (pw.KW - 1) - 1) // stride + 1
         if out is None:
-            out = self.fmap(name, x.N, OH, OW, pw.Cout, out_ld)
+            out = self.fmap(name, x.N, OH, OW, pw.Cout, out_ld, fmt=fmt)
         d = ConvDesc()
         d.N, d.H, d.W, d.Cin, d.x_ld, d.x_coff = (n_images or x.N), x.H, x.W, x.C, x.ld, 0
         d.x_nstride, d.y_nstride, d.x_hstride = x_nstride, y_nstride, x_hstride
@@ -241,12 +312,19 @@ class Engine:
         common = (stride in self.tc_strides and pw.groups == 1 and out.ld % 4 == 0 and out.coff % 4 == 0
                   and (res is None or (res.ld % 4 == 0 and res.coff % 4 == 0)) and (res2 is None or (res2.ld % 4 == 0 and res2.coff % 4 == 0))
                   and y_nstride % 4 == 0 and big and pw.Cout >= 32)
-        use_h = (impl == lib.IMPL_F16S and pw.w_h is not None and common and x.ld % 8 == 0 and x.coff % 8 == 0 and x_nstride % 8 == 0
-                 and x_hstride % 8 == 0 and (x.s is not None or (x.C % 4 == 0 and x.t is not None)))
+        split_only = x.t is None or out.t is None or (res is not None and res.t is None) or (res2 is not None and res2.t is None)
+        h_ok = (impl == lib.IMPL_F16S and pw.w_h is not None and stride in (1, 2) and pw.groups == 1 and out.ld % 4 == 0 and out.coff % 4 == 0
+                and (res is None or (res.ld % 4 == 0 and res.coff % 4 == 0)) and (res2 is None or (res2.ld % 4 == 0 and res2.coff % 4 == 0))
+                and y_nstride % 4 == 0 and x.ld % 8 == 0 and x.coff % 8 == 0 and x_nstride % 8 == 0
+                and x_hstride % 8 == 0 and (x.s is not None or (x.C % 4 == 0 and x.t is not None)))
+        use_h = h_ok and (common or split_only)                    # split-only operands exist only in the tensor-core format
+        if split_only and not use_h:
+            raise lib.TTError(f'conv {name}: an operand is stored as split planes only but the layer cannot run on the f16s kernel')
         use_tc = (impl in (lib.IMPL_TF32, lib.IMPL_3XTF32) and pw.w_tc is not None and common and x.ld % 4 == 0 and x.coff % 4 == 0
                   and x_nstride % 4 == 0 and x_hstride % 4 == 0)
         d.impl = impl if (use_tc or use_h) else lib.IMPL_SIMT
         if use_h:
+            self._cur_name = name
             xs = self.with_split(x)
         ws = None
         need = 0 if use_h else lib.load().tt_conv2d_workspace_bytes(C.byref(d))    # SIMT: split-K partials; tcgen05: 0
@@ -259,14 +337,29 @@ class Engine:
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        pres = _p(res.t, res.coff) if res is not None else None
-        pres2 = _p(res2.t, res2.coff) if res2 is not None else None
         if use_h:
-            px, xplane = _ps(xs)
-            pys, yplane = _ps(out) if out.s is not None else (None, 0)
-            lib.check(lib.load().tt_conv2d_f16s(C.byref(d), px, C.c_longlong(xplane), _p(pw.w_h), _p(pw.bias), pres, pres2,
-                                                _p(out.t, out.coff), pys, C.c_longlong(yplane), _stream()), f'tt_conv2d_f16s[{name}]')
+            io = lib.F16sIO()
+            io.x_split, io.x_plane = _ps(xs)[0], xs.s.numel() // 2
+            io.w_split, io.bias = _p(pw.w_h), _p(pw.bias)
+            for r, f32, sp, pl in ((res, 'res', 'res_split', 'res_plane'), (res2, 'res2', 'res2_split', 'res2_plane')):
+                if r is None:
+                    continue
+                if r.t is not None:
+                    setattr(io, f32, _p(r.t, r.coff))
+                else:
+                    setattr(io, sp, _p(r.s, r.coff)); setattr(io, pl, r.s.numel() // 2)
+            if out.t is not None:
+                io.y = _p(out.t, out.coff)
+            elif out.s.numel() // 2 <= (1 << 24):
+                # small split-only output: lend the kernel an fp32 workspace with the same element grid so that under-filled
+                # layers can still run split-K (partial sums are red.add-ed in fp32, the finish pass writes the planes)
+                io.y = _p(self.scratch_f32(out.s.numel() // 2), out.coff)
+            if out.s is not None:
+                io.y_split, io.y_plane = _p(out.s, out.coff), out.s.numel() // 2
+            lib.check(lib.load().tt_conv2d_f16s(C.byref(d), lib.ref(io), _stream()), f'tt_conv2d_f16s[{name}]')
         else:
+            pres = _p(res.t, res.coff) if res is not None else None
+            pres2 = _p(res2.t, res2.coff) if res2 is not None else None
             lib.check(lib.load().tt_conv2d(
                 C.byref(d), _p(x.t, x.coff), _p(pw.w_tc if use_tc else pw.w), _p(pw.bias), pres, pres2,
                 None, None, _p(out.t, out.coff), _p(ws), _stream()), f'tt_conv2d[{name}]')
@@ -334,7 +427,7 @@ class Engine:
         N, Cc, H, W = x.shape
         cpad = cpad or Cc
         out = self.fmap(name, N, H, W, cpad)
-        lib.call('tt_nchw_to_nhwc', _p(x), _p(out.t), N, Cc, H, W, out.ld, 0, cpad)
+        lib.call('tt_nchw_to_nhwc', _p(x), _p(_t(out)), N, Cc, H, W, out.ld, 0, cpad)
         return self.sync_split(out)
 
     def nchw_to_nhwc_padded(self, x, name, cpad, top, bottom, left, right):
@@ -347,54 +440,57 @@ class Engine:
 
     def nhwc_to_nchw(self, x, name):
         out = self.buf(name, (x.N, x.C, x.H, x.W))
-        lib.call('tt_nhwc_to_nchw', _p(x.t, x.coff), x.ld, 0, _p(out), x.N, x.C, x.H, x.W)
+        lib.call('tt_nhwc_to_nchw', _p(_t(x), x.coff), x.ld, 0, _p(out), x.N, x.C, x.H, x.W)
         return out
 
-    def maxpool3x3s2(self, x, name):
+    def maxpool3x3s2(self, x, name, fmt=None):
         assert x.ld == x.C and x.coff == 0
-        out = self.fmap(name, x.N, (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1, x.C)
-        lib.call('tt_maxpool3x3s2', _p(x.t), _p(out.t), x.N, x.H, x.W, x.C)
-        return self.sync_split(out)
+        self.need_f32(x, 'maxpool3x3s2')
+        out = self.out_map(name, x.N, (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1, x.C, fmt)
+        lib.call('tt_maxpool3x3s2', _p(_t(x)), _p(_t(out)), x.N, x.H, x.W, x.C)
+        return self.finish_out(out)
 
-    def upsample2x(self, x, name):
+    def upsample2x(self, x, name, fmt=None):
         assert x.ld == x.C and x.coff == 0
-        out = self.fmap(name, x.N, 2 * x.H, 2 * x.W, x.C)
-        lib.call('tt_upsample2x_bilinear_ac', _p(x.t), _p(out.t), x.N, x.H, x.W, x.C)
-        return self.sync_split(out)
+        self.need_f32(x, 'upsample2x')
+        out = self.out_map(name, x.N, 2 * x.H, 2 * x.W, x.C, fmt)
+        lib.call('tt_upsample2x_bilinear_ac', _p(_t(x)), _p(_t(out)), x.N, x.H, x.W, x.C)
+        return self.finish_out(out)
 
     def global_avgpool(self, x, name):
         out = self.fmap(name, x.N, 1, 1, x.C)
-        lib.call('tt_global_avgpool', _p(x.t, x.coff), x.ld, 0, _p(out.t), x.N, x.H * x.W, x.C)
+        lib.call('tt_global_avgpool', _p(_t(x), x.coff), x.ld, 0, _p(_t(out)), x.N, x.H * x.W, x.C)
         return self.sync_split(out)
 
     def broadcast_rows(self, v, out):
-        lib.call('tt_broadcast_rows', _p(v.t, v.coff), _p(out.t, out.coff), out.N, out.H * out.W, out.C, out.ld, 0)
+        lib.call('tt_broadcast_rows', _p(_t(v), v.coff), _p(_t(out), out.coff), out.N, out.H * out.W, out.C, out.ld, 0)
         return self.sync_split(out)
 
-    def se_gate(self, x, g, name):
+    def se_gate(self, x, g, name, fmt=None):
         assert x.ld == x.C and x.coff == 0 and g.ld == g.C
-        out = self.fmap(name, x.N, x.H, x.W, x.C)
-        lib.call('tt_se_gate', _p(x.t), _p(g.t), _p(out.t), x.N, x.H * x.W, x.C)
-        return self.sync_split(out)
+        self.need_f32(x, 'se_gate')
+        out = self.out_map(name, x.N, x.H, x.W, x.C, fmt)
+        lib.call('tt_se_gate', _p(_t(x)), _p(_t(g)), _p(_t(out)), x.N, x.H * x.W, x.C)
+        return self.finish_out(out)
 
     def se_pool(self, x, name):
         assert x.ld == x.C and x.coff == 0
         out = self.fmap(name, x.N, 1, 1, x.C)
-        lib.call('tt_se_pool', _p(x.t), _p(out.t), x.N, x.H * x.W, x.C)
+        lib.call('tt_se_pool', _p(_t(x)), _p(_t(out)), x.N, x.H * x.W, x.C)
         return self.sync_split(out)
 
     def se_apply(self, x, g, shortcut, out=None, name=None):
         assert x.ld == x.C and x.coff == 0
         if out is None:
             out = self.fmap(name, x.N, x.H, x.W, x.C)
-        lib.call('tt_se_apply', _p(x.t), _p(g.t), _p(shortcut.t, shortcut.coff), shortcut.ld, 0, _p(out.t, out.coff),
+        lib.call('tt_se_apply', _p(_t(x)), _p(_t(g)), _p(_t(shortcut), shortcut.coff), shortcut.ld, 0, _p(_t(out), out.coff),
                  out.ld, 0, x.N, x.H * x.W, x.C)
         return self.sync_split(out)
 
     def anti_transpose(self, x, name):
         assert x.ld == x.C and x.coff == 0 and x.H == x.W
         out = self.fmap(name, x.N, x.H, x.W, x.C)
-        lib.call('tt_anti_transpose', _p(x.t), _p(out.t), x.N, x.H, x.C)
+        lib.call('tt_anti_transpose', _p(_t(x)), _p(_t(out)), x.N, x.H, x.C)
         return self.sync_split(out)
 
     def copy_cols(self, src, dst, rdiv=1, rmod=None):
@@ -402,14 +498,29 @@ class Engine:
         rows = dst.rows()
         rmod = rmod if rmod is not None else max(src.rows(), 1)
         assert src.C == dst.C
-        lib.call('tt_copy2d', _p(src.t, src.coff), src.ld, _p(dst.t, dst.coff), dst.ld, rows, src.C, rdiv, rmod)
+        if dst.t is None and src.t is not None and src.s is None and rdiv == 1 and rmod >= rows:
+            if (src.C | src.coff | src.ld | dst.coff | dst.ld) % 4:
+                raise lib.TTError('copy_cols: fp32 -> split planes needs 4-column alignment')
+            lib.call('tt_split_f16', _p(src.t, src.coff), C.c_longlong(src.ld), _p(dst.s, dst.coff), C.c_longlong(dst.s.numel() // 2),
+                     C.c_longlong(dst.ld), C.c_longlong(rows), src.C, None)
+            return dst
+        if dst.t is None or src.t is None:
+            # plane-to-plane copy (both maps are stored as split planes): two halves travel as one 4-byte word
+            if src.s is None or dst.s is None or (src.C | src.ld | src.coff | dst.ld | dst.coff) % 2:
+                raise lib.TTError('copy_cols: a split-only map can only be copied from / to split planes (even offsets)')
+            for pl_s, pl_d in ((0, 0), (src.s.numel() // 2, dst.s.numel() // 2)):
+                lib.call('tt_copy2d', _p(src.s, src.coff + pl_s), src.ld // 2, _p(dst.s, dst.coff + pl_d), dst.ld // 2, rows, src.C // 2, rdiv, rmod)
+            if dst.t is not None:                                   # the destination also keeps an fp32 copy: rebuild it from its planes
+                self.merge_split(dst)
+            return dst
+        lib.call('tt_copy2d', _p(_t(src), src.coff), src.ld, _p(_t(dst), dst.coff), dst.ld, rows, src.C, rdiv, rmod)
         return self.sync_split(dst)
 
     def layernorm(self, x, gamma, beta, out=None, name=None, out_ld=None, row_count=None):
         xr = x.as_rows()
         if out is None:
             out = self.fmap(name, xr.N, 1, 1, xr.C, out_ld, zero=True)
-        lib.call('tt_layernorm', _p(xr.t, xr.coff), xr.ld, _p(gamma), _p(beta), _p(out.t, out.coff), out.ld, xr.N, xr.C,
+        lib.call('tt_layernorm', _p(_t(xr), xr.coff), xr.ld, _p(gamma), _p(beta), _p(_t(out), out.coff), out.ld, xr.N, xr.C,
                  _p(row_count))
         return self.sync_split(out)
 
@@ -418,8 +529,8 @@ class Engine:
         if out is None:
             out = self.fmap(name, a.N, a.H, a.W, a.C)
         o_ = out.as_rows()
-        lib.call('tt_eltwise', op, act, _p(a_.t, a_.coff), a_.ld, _p(b_.t, b_.coff) if b_ else None, b_.ld if b_ else 0,
-                 _p(c_.t, c_.coff) if c_ else None, c_.ld if c_ else 0, _p(o_.t, o_.coff), o_.ld, a_.N, a_.C)
+        lib.call('tt_eltwise', op, act, _p(_t(a_), a_.coff), a_.ld, _p(_t(b_), b_.coff) if b_ else None, b_.ld if b_ else 0,
+                 _p(_t(c_), c_.coff) if c_ else None, c_.ld if c_ else 0, _p(_t(o_), o_.coff), o_.ld, a_.N, a_.C)
         return self.sync_split(out)
 
     def fill(self, t, v=0.0):

@@ -30,6 +30,14 @@ class ConvDesc(C.Structure):
                                         'res2_ld', 'res2_coff', 'taps', 'M', 'impl')]
 
 
+class F16sIO(C.Structure):
+    """tt_f16s_io (include/tt_b200.h): the pointers of one tt_conv2d_f16s call."""
+    _fields_ = [('x_split', C.c_void_p), ('x_plane', C.c_longlong), ('w_split', C.c_void_p), ('bias', C.c_void_p),
+                ('res', C.c_void_p), ('res_split', C.c_void_p), ('res_plane', C.c_longlong),
+                ('res2', C.c_void_p), ('res2_split', C.c_void_p), ('res2_plane', C.c_longlong),
+                ('y', C.c_void_p), ('y_split', C.c_void_p), ('y_plane', C.c_longlong)]
+
+
 class LiftSplatDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ('B', 'N', 'D', 'fH', 'fW', 'C', 'ld_d', 'd_coff', 'ld_c', 'c_coff')] + \
                [('lower', C.c_float * 3), ('size', C.c_float * 3)] + \
@@ -91,7 +99,7 @@ EXPORTS = [
     'tt_maxpool3x3s2', 'tt_upsample2x_bilinear_ac', 'tt_global_avgpool', 'tt_broadcast_rows', 'tt_se_gate', 'tt_se_pool',
     'tt_se_apply', 'tt_anti_transpose', 'tt_copy2d', 'tt_layernorm', 'tt_eltwise', 'tt_fill', 'tt_dcn_im2col',
     'tt_voxelize_workspace_bytes', 'tt_voxelize_mean', 'tt_rulebook_workspace_bytes', 'tt_sparse_rulebook',
-    'tt_sparse_conv', 'tt_sparse_to_bev', 'tt_conv2d_f16s', 'tt_split_f16', 'tt_f16s_saturation_count', 'tt_sparse_conv_f16s', 'tt_look_project', 'tt_look_rebatch', 'tt_msda_forward', 'tt_look_reduce', 'tt_gru_input',
+    'tt_sparse_conv', 'tt_sparse_to_bev', 'tt_conv2d_f16s', 'tt_split_f16', 'tt_merge_f16', 'tt_f16s_saturation_count', 'tt_sparse_conv_f16s', 'tt_look_project', 'tt_look_rebatch', 'tt_msda_forward', 'tt_look_reduce', 'tt_gru_input',
 ]
 
 
@@ -106,6 +114,11 @@ def _p(t, off=0):
     if not t.is_cuda:
         raise TTError('tt_b200 ops need CUDA tensors (there is no CPU fallback)')
     return C.c_void_p(t.data_ptr() + off * t.element_size())
+
+
+def ref(struct):
+    """pointer to a ctypes struct for a C-ABI call."""
+    return C.byref(struct)
 
 
 def require_cuda(dev):

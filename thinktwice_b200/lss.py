@@ -140,14 +140,14 @@ class LSS(nn.Module):
     # ------------------------------------------------------------------ sub-graphs
     def _backbone(self, x):
         e, w = self.eng, self.w
-        x = e.maxpool3x3s2(x, 'rs.pool')
+        x = e.maxpool3x3s2(x, 'rs.pool', fmt='s')
         outs = []
         for bi, blk in enumerate(self.blocks):
-            y = e.conv(x, blk['c1'], name='rs.y1', act=ACT_RELU)
-            y = e.conv(y, blk['c2'], name='rs.y2', stride=blk['stride'], pad=1, act=ACT_RELU)
-            idt = x if blk['down'] is None else e.conv(x, blk['down'], name='rs.idt', stride=blk['stride'])
+            y = e.conv(x, blk['c1'], name='rs.y1', act=ACT_RELU, fmt='s')
+            y = e.conv(y, blk['c2'], name='rs.y2', stride=blk['stride'], pad=1, act=ACT_RELU, fmt='s')
+            idt = x if blk['down'] is None else e.conv(x, blk['down'], name='rs.idt', stride=blk['stride'], fmt='s')
             name = f"rs.c{blk['stage'] + 2}" if blk['last'] else f'rs.o{bi % 2}'
-            x = e.conv(y, blk['c3'], name=name, act=ACT_RELU, res=idt)
+            x = e.conv(y, blk['c3'], name=name, act=ACT_RELU, res=idt, fmt='s')
             if blk['last']:
                 outs.append(x)
         return outs
@@ -155,14 +155,14 @@ class LSS(nn.Module):
     def _pafpn(self, c):
         e, w = self.eng, self.w
         lat = [None] * 4
-        lat[3] = e.conv(c[3], w['lateral_convs'][3], name='fpn.lat3')
+        lat[3] = e.conv(c[3], w['lateral_convs'][3], name='fpn.lat3', fmt='s')
         for i in (2, 1, 0):                                            # top-down, nearest x2 fused as residual
-            lat[i] = e.conv(c[i], w['lateral_convs'][i], name=f'fpn.lat{i}', res=lat[i + 1], res_mode=lib.RES_UP2)
-        inter = [e.conv(lat[i], w['fpn_convs'][i], name=f'fpn.int{i}', pad=1) for i in range(4)]
+            lat[i] = e.conv(c[i], w['lateral_convs'][i], name=f'fpn.lat{i}', res=lat[i + 1], res_mode=lib.RES_UP2, fmt='s')
+        inter = [e.conv(lat[i], w['fpn_convs'][i], name=f'fpn.int{i}', pad=1, fmt='s') for i in range(4)]
         for i in range(3):                                             # bottom-up: inter[i+1] += down(inter[i])
             inter[i + 1] = e.conv(inter[i], w['downsample_convs'][i], out=inter[i + 1], name=f'fpn.down{i}', stride=2,
                                   pad=1, res=inter[i + 1])
-        outs = [inter[0]] + [e.conv(inter[i], w['pafpn_convs'][i - 1], name=f'fpn.out{i}', pad=1) for i in (1, 2, 3)]
+        outs = [inter[0]] + [e.conv(inter[i], w['pafpn_convs'][i - 1], name=f'fpn.out{i}', pad=1, fmt='s') for i in (1, 2, 3)]
         return outs
 
     def _se_vec(self, m, which):
@@ -181,7 +181,7 @@ class LSS(nn.Module):
         e.conv(cx, w['context_conv'], out=merge_in.slice(0, self.output_channels), name='dn.context')
         y = e.se_gate(x, gd, 'dn.dx')
         for i, (c1, c2) in enumerate(w['bb']):                          # 3 x BasicBlock
-            t = e.conv(y, c1, name='dn.bb.t', pad=1, act=ACT_RELU)
+            t = e.conv(y, c1, name='dn.bb.t', pad=1, act=ACT_RELU, fmt='s')
             y = e.conv(t, c2, name=f'dn.bb.o{i % 2}', pad=1, act=ACT_RELU, res=y)
         cat = e.fmap('dn.aspp.cat', BN, H, W, 5 * self.mid)
         for i, dil in enumerate([1, 6, 12, 18]):
@@ -200,13 +200,13 @@ class LSS(nn.Module):
         for g, wg in enumerate(w['dcn']):                               # grouped conv = one dense GEMM per group slice
             e.conv(col.slice(g * cg, cg), wg, out=yd.slice(g * wg.Cout, wg.Cout), name='dn.dcn.out')
         y = yd
-        return e.conv(y, w['depth_out'], name='dn.depth')
+        return e.conv(y, w['depth_out'], name='dn.depth', fmt='f')
 
     def _upcat(self, x, skip, ups, name):
         """cat[ConvTranspose2d_k2s2(x), skip] into one buffer (lss.py:254-256)."""
         e = self.eng
         cu = ups[0][0].Cout
-        cat = e.fmap(name, x.N, 2 * x.H, 2 * x.W, cu + skip.C)
+        cat = e.fmap(name, x.N, 2 * x.H, 2 * x.W, cu + skip.C, fmt='s')
         up = cat.slice(0, cu)
         for i in range(2):
             for j in range(2):
@@ -216,12 +216,12 @@ class LSS(nn.Module):
 
     def _unet(self, f):
         e, w = self.eng, self.w
-        d = e.conv(self._upcat(f[3], f[2], w['u4_up'], 'un.cat4'), w['u4_conv'], name='un.d4', pad=1, act=ACT_RELU)
-        d = e.conv(self._upcat(d, f[1], w['u3_up'], 'un.cat3'), w['u3_conv'], name='un.d3', pad=1, act=ACT_RELU)
+        d = e.conv(self._upcat(f[3], f[2], w['u4_up'], 'un.cat4'), w['u4_conv'], name='un.d4', pad=1, act=ACT_RELU, fmt='s')
+        d = e.conv(self._upcat(d, f[1], w['u3_up'], 'un.cat3'), w['u3_conv'], name='un.d3', pad=1, act=ACT_RELU, fmt='s')
         d = e.conv(self._upcat(d, f[0], w['u2_up'], 'un.cat2'), w['u2_conv'], name='un.d2', pad=1, act=ACT_RELU)
-        d = e.upsample2x(d, 'un.up0')
-        d = e.conv(d, w['u0_a'], name='un.d0a', pad=1, act=ACT_RELU)
-        d = e.conv(d, w['u0_b'], name='un.d0b', pad=1)
+        d = e.upsample2x(d, 'un.up0', fmt='s')
+        d = e.conv(d, w['u0_a'], name='un.d0a', pad=1, act=ACT_RELU, fmt='s')
+        d = e.conv(d, w['u0_b'], name='un.d0b', pad=1, fmt='s')
         return e.conv(d, w['seg_last'], name='seg').slice(0, self.seg_classes)
 
     def _seg_to_feat(self, seg, out):
@@ -230,7 +230,7 @@ class LSS(nn.Module):
         spec = [(1, 1), (1, 1), (3, 2), (1, 1), (3, 2), (1, 1), (3, 2)]
         for i, (k, s) in enumerate(spec):
             last = i == len(spec) - 1
-            x = e.conv(x, w['s2f'][i], out=out if last else None, name=f's2f.{i}', stride=s, pad=k // 2, act=ACT_RELU)
+            x = e.conv(x, w['s2f'][i], out=out if last else None, name=f's2f.{i}', stride=s, pad=k // 2, act=ACT_RELU, fmt='s')
             x = x.slice(0, self.s2f_channels[i]) if not last else x
         return x
 
@@ -252,18 +252,18 @@ class LSS(nn.Module):
             pbs = e.buf('img.nhwc#s8', (2, rows * 8), torch.float16, zero=True)
             lib.call('tt_split_f16', _p(pb), C.c_longlong(4), _p(pbs), C.c_longlong(rows * 8), C.c_longlong(8), C.c_longlong(rows), 4, None)
             x = e.conv(FMap(None, B * N, H0 + 6, W0, 64, ld=8, s=pbs), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
-                       x_hstride=Wp * 8, x_nstride=(H0 + 6) * Wp * 8)
+                       x_hstride=Wp * 8, x_nstride=(H0 + 6) * Wp * 8, fmt='f')    # only the max-pool (an fp32 kernel) reads it
         else:
             x = e.conv(FMap(pb, B * N, H0 + 6, W0, 32, ld=4), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
                        x_hstride=Wp * 4, x_nstride=(H0 + 6) * Wp * 4)
         fpn = self._pafpn(self._backbone(x))
-        src = e.conv(fpn[2], w['neck_conv'], name='img_feats')
+        src = e.conv(fpn[2], w['neck_conv'], name='img_feats', fmt='s')
         mlp_in = e.wrap(e.static('in.mlp_in').view(B * N, 1, 1, 24))
-        merge_in = e.fmap('merge_in', B * N, src.H, src.W, self.output_channels + 128)
+        merge_in = e.fmap('merge_in', B * N, src.H, src.W, self.output_channels + 128, fmt='s')
         depth = self._depthnet(src, mlp_in, merge_in)
         seg = self._unet(fpn)
         self._seg_to_feat(seg, merge_in.slice(self.output_channels, 128))
-        feat = e.conv(merge_in, w['merge'], name='img_feature', pad=1)
+        feat = e.conv(merge_in, w['merge'], name='img_feature', pad=1, fmt='f')
         m = e.static(f'in.lift_mats.{s}')                           # staged by stage(): ida^-1 and sensor2ego @ intrin^-1
         d = LiftSplatDesc()
         d.B, d.N, d.D, d.fH, d.fW, d.C = B, N, self.depth_channels, src.H, src.W, self.output_channels
