@@ -99,6 +99,41 @@ def cpu_oracle_worker(max_frames):
             print(f'FRAME {time.perf_counter() - t0:.3f}', flush=True)
 
 
+def make_weights_worker(out):
+    """child process (`--impl make-weights`): the synthetic checkpoint of SURVEY.md §8d — seeded random init of every layer, then
+    BatchNorm running statistics set by ONE calibration pass of the CPU oracle over a synthetic frame and frozen, so that activations
+    are O(1) like a trained network's (a raw random init drives this network's activations to ~1e6).  Written as an mmcv-style
+    checkpoint file; the timed process only ever LOADS it (thinktwice_agent.py:170 path) and never imports oracle/."""
+    import torch
+    from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
+    from thinktwice_b200.config import Config, DEFAULT_CONFIG
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(DEFAULT_CONFIG)
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
+    oracle = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'}).eval()
+    init_oracle_weights(oracle, 0)
+    calibrate_bn(oracle, make_batch(cfg, 1, seed=0))
+    tmp = out + f'.tmp{os.getpid()}'
+    torch.save({'meta': {'recipe': 'SURVEY.md 8d: seeded init + one oracle BN-calibration pass'}, 'state_dict': oracle.state_dict()}, tmp)
+    os.replace(tmp, out)
+
+
+def synthetic_checkpoint(rank):
+    """path of the synthetic calibrated checkpoint; rank 0 creates it (in a child process) when it is not there yet."""
+    path = os.path.join(os.environ.get('TT_B200_CKPT_DIR', '/tmp'), 'tt_b200_synthetic_seed0.pth')
+    if not os.path.exists(path):
+        if rank == 0:
+            env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS')}
+            subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'make-weights', '--out', path], check=True, env=env,
+                           stdout=subprocess.DEVNULL)
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > 900:
+                raise RuntimeError(f'{path} did not appear')
+            time.sleep(1.0)
+    return path
+
+
 def cpu_oracle(max_frames, budget_s):
     """frames/s of the CPU restatement on a bounded sample (<= max_frames B=1 frames, <= budget_s seconds)."""
     env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS')}
@@ -140,7 +175,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step (32 = the throughput configs[2] / configs[3])')
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-worker'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-worker', 'make-weights'])
+    ap.add_argument('--out', default=None, help='(make-weights) checkpoint file to write')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-latency', action='store_true', help='skip the extra B=1 latency measurement')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
@@ -155,11 +191,13 @@ def main():
 
     if args.impl == 'reference-worker':
         return cpu_oracle_worker(args.steps)
+    if args.impl == 'make-weights':
+        return make_weights_worker(args.out)
     import torch
     from thinktwice_b200.config import Config, DEFAULT_CONFIG
     cfg = Config.fromfile(DEFAULT_CONFIG)
     base = {'metric': METRIC, 'unit': 'frames/s', 'n_gpus': args.gpus, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'data': 'synthetic (seeded N(0,1) images, synthetic LiDAR, random-init weights)',
+            'vs_baseline': None, 'data': 'synthetic (seeded N(0,1) images, synthetic LiDAR; seeded random-init weights with BatchNorm statistics calibrated by one oracle pass, SURVEY 8d, loaded from a checkpoint file)',
             'config': {'workload': workload(args.batch, args.gpus), 'frames_per_gpu_per_step': args.batch, 'global_batch': args.batch * args.gpus,
                        'refine_num': 5, 'conv_engine': args.conv, 'cuda_graph': not args.no_graph,
                        'parallelism': f'dp{args.gpus} (frames sharded, one NCCL all_gather of pred_wp)',
@@ -190,6 +228,8 @@ def main():
     from thinktwice_b200.synthetic import make_batch
 
     model = build_model(cfg.model)
+    ckpt = torch.load(synthetic_checkpoint(rank), map_location='cpu', weights_only=False)      # the agent's checkpoint path
+    model.load_state_dict(ckpt['state_dict'])
     model.prepare(dev, impl={'simt': lib.IMPL_SIMT, '3xtf32': lib.IMPL_3XTF32, 'tf32': lib.IMPL_TF32, 'f16s': lib.IMPL_F16S}[args.conv])
     B = args.batch
     host = make_batch(cfg, B, seed=100 + rank)                    # every rank owns different frames (weak scaling)

@@ -124,7 +124,7 @@ struct HArgs {
   int splits, k_per;     // split-K: K stages per split
 };
 
-template <int BN, int STAGES, bool GATHER>
+template <int BN, int STAGES, bool GATHER, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -155,11 +155,14 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = d.KH * d.KW;
   const int k_iters = taps * p.n_slabs;
-  const uint32_t rank = cluster_ctarank();
-  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  // PAIR: CTA pairs (cluster of 2) walk two M tiles of the same N tile in lockstep and multicast weight halves to each other;
+  // !PAIR: every CTA is on its own (loads the whole weight slab itself, no cross-CTA barriers) — measured alternative
+  constexpr int CL = PAIR ? 2 : 1;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int pair0 = blockIdx.x / CL, pair_step = gridDim.x / CL;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], 2); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -169,7 +172,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int c = min(p.pair_count[t], p.pair_cap);
       sp_cnt[t] = c;
       sp_first[t] = acc;
-      acc += ((c + BM - 1) / BM + 1) / 2;
+      acc += ((c + BM - 1) / BM + CL - 1) / CL;
     }
     sp_first[p.kvol] = acc;
   }
@@ -182,7 +185,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_pairs = (GATHER ? sp_first[p.kvol] : (p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+  const int total_pairs = (GATHER ? sp_first[p.kvol] : (p.m_tiles + CL - 1) / CL) * p.n_tiles * p.splits;
   auto decode = [&](int pt, int& nt, int& mt, int& tap, int& count, int& kb, int& ke) {
     const int ks = pt % p.splits;
     pt /= p.splits;
@@ -193,10 +196,26 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tap = 0; count = 0;
     if (GATHER) {
       while (sp_first[tap + 1] <= pm) ++tap;
-      mt = 2 * (pm - sp_first[tap]) + (int)rank;
+      mt = CL * (pm - sp_first[tap]) + (int)rank;
       count = sp_cnt[tap];
     } else {
-      mt = 2 * pm + (int)rank;
+      mt = CL * pm + (int)rank;
+    }
+  };
+
+  // weight slab of one stage: hi plane then lo' plane, BN rows each.  PAIR: this CTA loads its half of each plane and multicasts
+  // it to both CTAs of the pair; !PAIR: it loads both halves for itself.
+  auto load_weights = [&](uint8_t* st, uint64_t* bar, int k0, int tap, int n0) {
+    uint8_t* bh = st + 2 * A_BYTES;
+    if (PAIR) {
+      tma_load_4d_mc(bh + rank * (B_BYTES / 2), &map_b, bar, k0, tap, n0 + (int)rank * (BN / 2), 0, 3);
+      tma_load_4d_mc(bh + B_BYTES + rank * (B_BYTES / 2), &map_b, bar, k0, tap, n0 + (int)rank * (BN / 2), 1, 3);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tma_load_4d(bh + h * (B_BYTES / 2), &map_b, bar, k0, tap, n0 + h * (BN / 2), 0);
+        tma_load_4d(bh + B_BYTES + h * (B_BYTES / 2), &map_b, bar, k0, tap, n0 + h * (BN / 2), 1);
+      }
     }
   };
 
@@ -221,8 +240,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint8_t* st = smem + s * STAGE_BYTES;
         if (lane == 0) {
           mbar_expect_tx(&full[s], txb);
-          tma_load_4d_mc(st + 2 * A_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], it * KE, tap, n0 + (int)rank * (BN / 2), 0, 3);
-          tma_load_4d_mc(st + 2 * A_BYTES + B_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], it * KE, tap, n0 + (int)rank * (BN / 2), 1, 3);
+          load_weights(st, &full[s], it * KE, tap, n0);
         }
         const int c0 = it * KE;
 #pragma unroll
@@ -275,8 +293,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               tma_load_5d(st + A_BYTES, &map_a, &full[s], slab * KE, cw, ch, cn, 1);
             }
           }
-          tma_load_4d_mc(st + 2 * A_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], slab * KE, tap, n0 + (int)rank * (BN / 2), 0, 3);
-          tma_load_4d_mc(st + 2 * A_BYTES + B_BYTES + rank * (B_BYTES / 2), &map_b, &full[s], slab * KE, tap, n0 + (int)rank * (BN / 2), 1, 3);
+          load_weights(st, &full[s], slab * KE, tap, n0);
         }
       }
     }
@@ -313,7 +330,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               umma_f16(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);      // lo'*hi
             }
             first = false;
-            tcgen05_commit_mc(&empty[s], 3);
+            if (PAIR) tcgen05_commit_mc(&empty[s], 3); else tcgen05_commit(&empty[s]);
           }
           tcgen05_commit(&acc_full[b]);
         }
@@ -596,13 +613,25 @@ int num_sms_cached() {
 }
 constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;
 
-template <int BN, int STAGES, bool GATHER>
-cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
+template <int BN, int STAGES, bool GATHER, bool PAIR>
+cudaError_t launch_f16s_v(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
   constexpr int smem = STAGES * (2 * BM * KE * 2 + 2 * BN * KE * 2) + 1024 + EPI_BYTES;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
   cfg.dynamicSmemBytes = smem;
-  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER>, ma, mb, a);
+  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR>, ma, mb, a);
+}
+// work items / grid for `tiles` M tiles; debug bit 0x100000 selects the unpaired variant
+template <int BN, int STAGES, bool GATHER>
+cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a, long long m_units) {
+  const bool pair = !(g_tt_debug & 0x100000);
+  const int cl = pair ? 2 : 1;
+  const int num_sms = num_sms_cached() - ((g_tt_debug >> 8) & 0xFF);
+  const long long items = ((m_units + cl - 1) / cl) * a.n_tiles * a.splits;
+  const long long max_items = num_sms / cl;
+  cfg.gridDim = dim3((unsigned)(cl * (items < max_items ? items : max_items)));
+  cfg.attrs[0].val.clusterDim.x = cl;
+  return pair ? launch_f16s_v<BN, STAGES, GATHER, true>(cfg, ma, mb, a) : launch_f16s_v<BN, STAGES, GATHER, false>(cfg, ma, mb, a);
 }
 
 bool encode_weights(CUtensorMap* mb, const void* w_split, int Cin, int taps, int Cout, int BN) {
@@ -762,10 +791,7 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
     a.d.act = TT_ACT_NONE;
     a.d.res_mode = TT_RES_NONE;
   }
-  const long long pairs = (long long)((a.m_tiles + 1) / 2) * a.n_tiles * a.splits;
-  const long long max_pairs = (num_sms - ((g_tt_debug >> 8) & 0xFF)) / 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
   cfg.blockDim = dim3(NTHREADS);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -773,7 +799,7 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, false>(cfg, ma, mb, a) : launch_f16s<64, 4, false>(cfg, ma, mb, a);
+  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, false>(cfg, ma, mb, a, a.m_tiles) : launch_f16s<64, 4, false>(cfg, ma, mb, a, a.m_tiles);
   if (lerr != cudaSuccess) { tt_set_error("tt_conv2d_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_conv2d_f16s");
@@ -822,11 +848,7 @@ int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split
   a.n_tiles = tt_cdiv(d->Cout, BN);
   CUtensorMap mb;
   if (!encode_weights(&mb, w_split, d->Cin, d->kvol, d->Cout, BN)) return TT_ERR_CUDA;
-  const int num_sms = num_sms_cached();
-  const long long cap_pairs = (long long)d->kvol * ((tt_cdiv(d->pair_cap, BM) + 1) / 2) * a.n_tiles;
-  const long long max_pairs = num_sms / 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * (cap_pairs < max_pairs ? cap_pairs : max_pairs)));
   cfg.blockDim = dim3(NTHREADS);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -834,7 +856,8 @@ int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, true>(cfg, mb, mb, a) : launch_f16s<64, 4, true>(cfg, mb, mb, a);
+  const long long cap_units = (long long)d->kvol * tt_cdiv(d->pair_cap, BM);      // upper bound of gathered M tiles over all taps
+  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, true>(cfg, mb, mb, a, cap_units) : launch_f16s<64, 4, true>(cfg, mb, mb, a, cap_units);
   if (lerr != cudaSuccess) { tt_set_error("tt_sparse_conv_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_sparse_conv_f16s");

@@ -218,11 +218,32 @@ class EncoderDecoder(nn.Module):
         self._graphs = {}
         return self
 
+    def release_buffers(self):
+        """drop the activation arena, the staged inputs and every captured graph (the packed weights stay).  Buffers are keyed by
+        (name, shape) and never shrink, so a model that served one batch size keeps that arena until told otherwise; the forward
+        calls this itself when the batch size changes."""
+        e = self.eng
+        if e is None:
+            return
+        if getattr(self, '_graphs', None):
+            self._graphs.clear()
+        keep = {k: v for k, v in e.bufs.items() if k[0].startswith('w.')}
+        e.bufs.clear(); e.bufs.update(keep)
+        e.cur.clear(); e.last_buf.clear(); e.conv_ws.clear(); e._ws_retired.clear(); e._scratch.clear()
+        self.last_cam_feat = None
+        if e.device.type == 'cuda':
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+
     @torch.no_grad()
     def forward_inference(self, batch):
         if self.eng is None:
             self.prepare(batch['img'].device if batch['img'].is_cuda else 'cuda:0')
         self.epoch = 10000
+        B_now = batch['img'].shape[0]
+        if getattr(self, '_arena_B', B_now) != B_now:
+            self.release_buffers()                                 # one arena at a time: another batch size starts from scratch
+        self._arena_B = B_now
         key = self.stage(batch)
         if not getattr(self, 'use_graph', False):
             return self._own(self._device_forward())
