@@ -257,6 +257,15 @@ int tt_sparse_conv(const tt_sparse_conv_desc* d, const float* feats_in, const fl
 int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split, long long in_plane, const void* w_split,
                         const float* bias, const float* res, const int* pairs_in, const int* pairs_out, const int* pair_count,
                         const int* out_count, float* feats_out, void* out_split, long long out_plane, tt_stream_t stream);
+/* Output-stationary sparse convolution on scaled-split fp16 operands: ONE launch, no atomics.  A work item is a tile of 128 output
+ * rows; K runs over all kvol taps through the neighbour table `nbr` [cap_out][kvol] (input row under each tap, -1 = none: a zero
+ * row), so the sum of an output row is formed in TMEM in a fixed order and stored once with bias + residual + activation fused
+ * (fp32 rows `io->y` and / or split planes `io->y_split`; residual as fp32 `io->res` or planes `io->res_split`).  Pays for empty
+ * (row, tap) slots with zero rows — the better form once a fair share of the taps is populated (dilated / dense-ish clouds);
+ * tt_sparse_conv_f16s (tap-major pair lists, red.add) is the form for very sparse neighbourhoods.  io->x_split = input planes
+ * [2][cap_in][in_ld]; w_split = [2][Cout][kvol][Cin8]; d->cap_out = row capacity, *out_count = rows that exist. */
+int tt_sparse_conv_os_f16s(const tt_sparse_conv_desc* d, const tt_f16s_io* io, const int* nbr, const int* out_count,
+                           tt_stream_t stream);
 /* dense()[N][C][D][H][W].view(N, C*D, H, W) (lidarnet.py:53-56) written channels-last, channel = c*D + z,
  * with the framework's anti-transpose (framework:246) folded in when asked; `dense` must be zero-filled. */
 int tt_sparse_to_bev(const float* feats, const int* coords, const int* count, int cap, int C, int D, int H, int W,

@@ -274,7 +274,8 @@ class Emu:
         out_count.flat()[0] = n_out
         ikeys = key(ic, ishape)
         srt, perm = torch.sort(ikeys)
-        pin, pout = pairs_in.flat().view(kvol, -1), pairs_out.flat().view(kvol, -1)
+        pin = pairs_in.flat().view(kvol, -1) if pairs_in else None
+        pout = pairs_out.flat().view(kvol, -1) if pairs_out else None
         for ti, t in enumerate(taps):
             if d.subm:
                 src = oc[:, 1:] + torch.tensor(t) - torch.tensor([kk // 2 for kk in k])
@@ -286,9 +287,10 @@ class Emu:
             hit = ok & (srt[pos] == sk) if srt.numel() else ok & False
             rows_out = torch.nonzero(hit).squeeze(1)
             m = rows_out.numel()
-            pin[ti, :m] = perm[pos[hit]].int()
-            pout[ti, :m] = rows_out.int()
-            pair_count.flat()[ti] = m
+            if pin is not None:
+                pin[ti, :m] = perm[pos[hit]].int()
+                pout[ti, :m] = rows_out.int()
+                pair_count.flat()[ti] = m
             if nbr:
                 nb = nbr.flat().view(-1, kvol)
                 nb[:n_out, ti] = -1
@@ -345,6 +347,39 @@ class Emu:
             hi, lo = _split_f16(o)
             out_split.flat().view(-1, d.out_ld)[:n_out, :d.Cout] = hi
             Ptr(out_split.t, out_split.off + out_plane).flat().view(-1, d.out_ld)[:n_out, :d.Cout] = lo
+        return 0
+
+    def tt_sparse_conv_os_f16s(self, d, io, nbr, out_count, stream):
+        """output-stationary form: out[m] = act(sum_tap W[tap] . in[nbr[m][tap]] + bias + res[m]), one launch."""
+        d = _desc(d)
+        self.launches += 1
+        n_out = int(out_count.flat()[0])
+        rows_in = io.x_plane // d.in_ld
+        fi = (io.x_split.flat().view(-1, d.in_ld)[:rows_in, :d.Cin].double() +
+              Ptr(io.x_split.t, io.x_split.off + io.x_plane).flat().view(-1, d.in_ld)[:rows_in, :d.Cin].double() / 2048.0)
+        c8 = -(-d.Cin // 8) * 8
+        planes = io.w_split.flat()[:2 * d.Cout * d.kvol * c8].view(2, d.Cout, d.kvol, c8).double()
+        wt = (planes[0] + planes[1] / 2048.0)[..., :d.Cin].permute(1, 2, 0)   # (kvol, Cin, Cout)
+        nb = nbr.flat().view(-1, d.kvol)[:n_out].long()
+        out = torch.zeros(n_out, d.Cout, dtype=torch.float64)
+        for t in range(d.kvol):
+            ok = nb[:, t] >= 0
+            if ok.any():
+                out[ok] += fi[nb[ok, t]] @ wt[t]
+        if io.bias:
+            out += io.bias.flat()[:d.Cout].double()
+        if io.res:
+            out += io.res.flat().view(-1, d.res_ld)[:n_out, :d.Cout].double()
+        elif io.res_split:
+            out += (io.res_split.flat().view(-1, d.res_ld)[:n_out, :d.Cout].double() +
+                    Ptr(io.res_split.t, io.res_split.off + io.res_plane).flat().view(-1, d.res_ld)[:n_out, :d.Cout].double() / 2048.0)
+        o = _act(out, d.act).float()
+        if io.y:
+            io.y.flat().view(-1, d.out_ld)[:n_out, :d.Cout] = o
+        if io.y_split:
+            hi, lo = _split_f16(o)
+            io.y_split.flat().view(-1, d.out_ld)[:n_out, :d.Cout] = hi
+            Ptr(io.y_split.t, io.y_split.off + io.y_plane).flat().view(-1, d.out_ld)[:n_out, :d.Cout] = lo
         return 0
 
     def tt_sparse_to_bev(self, feats, coords, count, cap, Cc, D, H, W, anti, dense, stream):

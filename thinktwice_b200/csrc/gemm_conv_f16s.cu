@@ -121,10 +121,16 @@ struct HArgs {
   const int* pairs_out;
   const int* pair_count;
   int kvol, pair_cap;
+  const int* nbr;        // output-stationary: [cap_rows][kvol] input row under each tap of an output row, -1 = none
+  const int* out_count;  // output-stationary: number of output rows (device scalar)
+  int cap_rows;
   int splits, k_per;     // split-K: K stages per split
 };
 
-template <int BN, int STAGES, bool GATHER, bool PAIR>
+// GM (gather mode): 0 = dense convolution (TMA box loads); 1 = tap-major sparse convolution (work item = one tap's pair tile,
+// red.add epilogue); 2 = output-stationary sparse convolution (work item = an output-row tile, K runs over ALL taps through the
+// neighbour table, plain fused epilogue — no atomics, no init / finish passes; pays for empty (row, tap) slots with zero rows).
+template <int BN, int STAGES, int GM, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -153,8 +159,10 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const tt_conv_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int taps = d.KH * d.KW;
+  constexpr bool GATHER = GM != 0;
+  const int taps = GM == 2 ? p.kvol : d.KH * d.KW;
   const int k_iters = taps * p.n_slabs;
+  const int os_rows = GM == 2 ? min(*p.out_count, p.cap_rows) : 0;     // output-stationary: rows that exist (device count)
   // PAIR: CTA pairs (cluster of 2) walk two M tiles of the same N tile in lockstep and multicast weight halves to each other;
   // !PAIR: every CTA is on its own (loads the whole weight slab itself, no cross-CTA barriers) — measured alternative
   constexpr int CL = PAIR ? 2 : 1;
@@ -166,7 +174,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (GATHER && threadIdx.x == 64) {
+  if (GM == 1 && threadIdx.x == 64) {
     int acc = 0;
     for (int t = 0; t < p.kvol; ++t) {
       const int c = min(p.pair_count[t], p.pair_cap);
@@ -185,7 +193,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_pairs = (GATHER ? sp_first[p.kvol] : (p.m_tiles + CL - 1) / CL) * p.n_tiles * p.splits;
+  const int os_tiles = (os_rows + BM - 1) / BM;
+  const int total_pairs = (GM == 1 ? sp_first[p.kvol] : ((GM == 2 ? os_tiles : p.m_tiles) + CL - 1) / CL) * p.n_tiles * p.splits;
   auto decode = [&](int pt, int& nt, int& mt, int& tap, int& count, int& kb, int& ke) {
     const int ks = pt % p.splits;
     pt /= p.splits;
@@ -194,7 +203,10 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     nt = pt % p.n_tiles;
     const int pm = pt / p.n_tiles;
     tap = 0; count = 0;
-    if (GATHER) {
+    if (GM == 2) {
+      mt = CL * pm + (int)rank;
+      count = os_rows;
+    } else if (GM == 1) {
       while (sp_first[tap + 1] <= pm) ++tap;
       mt = CL * (pm - sp_first[tap]) + (int)rank;
       count = sp_cnt[tap];
@@ -227,22 +239,33 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int nt, mt, tap, count, kb, ke;
       decode(pt, nt, mt, tap, count, kb, ke);
       const int n0 = nt * BN;
-      const int* pin = p.pairs_in + (long long)tap * p.pair_cap;
+      const int* pin = GM == 1 ? p.pairs_in + (long long)tap * p.pair_cap : nullptr;
       int rows[4];
+      if (GM == 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = mt * BM + lane + 32 * i;
-        rows[i] = m < count ? __ldg(pin + m) : -1;
+        for (int i = 0; i < 4; ++i) {
+          const int m = mt * BM + lane + 32 * i;
+          rows[i] = m < count ? __ldg(pin + m) : -1;
+        }
       }
       for (int it = kb; it < ke; ++it, ++ig) {
         const int s = ig % STAGES;
+        const int ktap = GM == 2 ? it / p.n_slabs : tap;            // output-stationary: the K walk visits every tap
+        const int slab = GM == 2 ? it - ktap * p.n_slabs : it;
+        if (GM == 2 && (slab == 0 || it == kb)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = mt * BM + lane + 32 * i;
+            rows[i] = m < count ? __ldg(p.nbr + (long long)m * p.kvol + ktap) : -1;       // -1: no input site under this tap
+          }
+        }
         mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
         uint8_t* st = smem + s * STAGE_BYTES;
         if (lane == 0) {
           mbar_expect_tx(&full[s], txb);
-          load_weights(st, &full[s], it * KE, tap, n0);
+          load_weights(st, &full[s], slab * KE, ktap, n0);
         }
-        const int c0 = it * KE;
+        const int c0 = slab * KE;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = lane + 32 * i;
@@ -353,7 +376,17 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int nch = (ke - kb + p.chunk - 1) / p.chunk;
       const bool real_tile = GATHER ? mt * BM < count : mt < p.m_tiles;
       const int n0 = nt * BN + half * HN;
-      if (GATHER) {
+      if (GM == 2) {
+        const int m = mt * BM + r;
+        const bool valid = m < count;
+        const long long r1 = (long long)m * d.res_ld + d.res_coff;
+        if (half == 0) {
+          row_y[r] = (long long)m * d.y_ld + d.y_coff;
+          row_r1[r] = r1;
+          row_r2[r] = 0;
+          row_flag[r] = valid ? 1 : 0;
+        }
+      } else if (GM == 1) {
         const int m = mt * BM + r;
         const bool valid = m < count;
         if (half == 0) {
@@ -473,7 +506,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             float4 o = make_float4(acc4[i].x + bv.x + ra[i].x + rb[i].x, acc4[i].y + bv.y + ra[i].y + rb[i].y,
                                    acc4[i].z + bv.z + ra[i].z + rb[i].z, acc4[i].w + bv.w + ra[i].w + rb[i].w);
             const long long eo = yo[i] + col;
-            if (GATHER || p.splits > 1) {                      // taps / K splits race on an output row: red.add (fp32 only)
+            if (GM == 1 || p.splits > 1) {                     // taps / K splits race on an output row: red.add (fp32 only)
               tt_red_add_v4(p.y + eo, o.x, o.y, o.z, o.w);
             } else {
               o = make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
@@ -613,7 +646,7 @@ int num_sms_cached() {
 }
 constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;
 
-template <int BN, int STAGES, bool GATHER, bool PAIR>
+template <int BN, int STAGES, int GATHER, bool PAIR>
 cudaError_t launch_f16s_v(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
   constexpr int smem = STAGES * (2 * BM * KE * 2 + 2 * BN * KE * 2) + 1024 + EPI_BYTES;
   static bool set = false;
@@ -622,7 +655,7 @@ cudaError_t launch_f16s_v(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const 
   return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR>, ma, mb, a);
 }
 // work items / grid for `tiles` M tiles; debug bit 0x100000 selects the unpaired variant
-template <int BN, int STAGES, bool GATHER>
+template <int BN, int STAGES, int GATHER>
 cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a, long long m_units) {
   const bool pair = !(g_tt_debug & 0x100000);
   const int cl = pair ? 2 : 1;
@@ -799,7 +832,7 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, false>(cfg, ma, mb, a, a.m_tiles) : launch_f16s<64, 4, false>(cfg, ma, mb, a, a.m_tiles);
+  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, 0>(cfg, ma, mb, a, a.m_tiles) : launch_f16s<64, 4, 0>(cfg, ma, mb, a, a.m_tiles);
   if (lerr != cudaSuccess) { tt_set_error("tt_conv2d_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_conv2d_f16s");
@@ -857,7 +890,7 @@ int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const long long cap_units = (long long)d->kvol * tt_cdiv(d->pair_cap, BM);      // upper bound of gathered M tiles over all taps
-  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, true>(cfg, mb, mb, a, cap_units) : launch_f16s<64, 4, true>(cfg, mb, mb, a, cap_units);
+  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, 1>(cfg, mb, mb, a, cap_units) : launch_f16s<64, 4, 1>(cfg, mb, mb, a, cap_units);
   if (lerr != cudaSuccess) { tt_set_error("tt_sparse_conv_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_sparse_conv_f16s");
@@ -865,6 +898,56 @@ int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split
                                                  static_cast<__half*>(out_split), out_plane);
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_sparse_conv_f16s(finish)");
+  return TT_OK;
+}
+
+int tt_sparse_conv_os_f16s(const tt_sparse_conv_desc* d, const tt_f16s_io* io, const int* nbr, const int* out_count, tt_stream_t stream) {
+  TT_REQUIRE(d && io && io->x_split && io->w_split && (io->y || io->y_split) && nbr && out_count, "tt_sparse_conv_os_f16s", "null argument");
+  TT_REQUIRE(!(io->res && io->res_split) && !io->res2 && !io->res2_split, "tt_sparse_conv_os_f16s", "one residual, fp32 or split planes");
+  if (d->Cin % 8 || d->Cout % 4 || d->in_ld % 8 || d->out_ld % 4 || d->Cin < 32 || d->Cout < 32 || d->kvol < 1 || io->x_plane % 8 || io->y_plane % 4 ||
+      (d->res_ld % 4) || io->res_plane % 4 ||
+      ((reinterpret_cast<uintptr_t>(io->x_split) | reinterpret_cast<uintptr_t>(io->w_split) | reinterpret_cast<uintptr_t>(io->y) |
+        reinterpret_cast<uintptr_t>(io->res) | reinterpret_cast<uintptr_t>(io->bias)) & 15) ||
+      ((reinterpret_cast<uintptr_t>(io->y_split) | reinterpret_cast<uintptr_t>(io->res_split)) & 7)) {
+    tt_set_error("tt_sparse_conv_os_f16s: needs Cin %% 8, Cout %% 4, Cin / Cout >= 32, in_ld %% 8, out_ld %% 4, 16-byte aligned pointers");
+    return TT_ERR_UNSUPPORTED;
+  }
+  if (d->cap_out <= 0) return TT_OK;
+  HArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d.N = a.d.H = a.d.W = a.d.OH = a.d.OW = a.d.yH = a.d.yW = 1;
+  a.d.KH = a.d.KW = a.d.stride = a.d.dil = a.d.groups = 1;
+  a.d.oy_mul = a.d.ox_mul = 1;
+  a.d.Cin = d->Cin; a.d.x_ld = d->in_ld; a.d.Cout = d->Cout; a.d.y_ld = d->out_ld;
+  a.d.act = d->act;
+  a.d.res_mode = (io->res || io->res_split) ? TT_RES_SAME : TT_RES_NONE;
+  a.d.res_ld = d->res_ld;
+  a.bias = io->bias; a.res = io->res;
+  a.res_s = static_cast<const __half*>(io->res_split); a.res_plane = io->res_plane;
+  a.y = io->y; a.ys = static_cast<__half*>(io->y_split); a.ys_plane = io->y_plane;
+  a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;
+  a.n_slabs = (d->Cin + KE - 1) / KE;
+  a.dbg = g_tt_debug & 0xFF;
+  a.gx = static_cast<const __half*>(io->x_split); a.gx_plane = io->x_plane; a.gx_ld = d->in_ld;
+  a.kvol = d->kvol; a.nbr = nbr; a.out_count = out_count; a.cap_rows = d->cap_out;
+  a.splits = 1; a.k_per = d->kvol * a.n_slabs;
+  const int BN = d->Cout > 64 ? 128 : 64;
+  a.n_tiles = tt_cdiv(d->Cout, BN);
+  CUtensorMap mb;
+  if (!encode_weights(&mb, io->w_split, d->Cin, d->kvol, d->Cout, BN)) return TT_ERR_CUDA;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const long long cap_units = tt_cdiv(d->cap_out, BM);
+  const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, 2>(cfg, mb, mb, a, cap_units) : launch_f16s<64, 4, 2>(cfg, mb, mb, a, cap_units);
+  if (lerr != cudaSuccess) { tt_set_error("tt_sparse_conv_os_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_sparse_conv_os_f16s");
   return TT_OK;
 }
 

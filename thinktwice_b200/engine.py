@@ -405,7 +405,18 @@ class Engine:
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if use_h:
+        if use_h and rule.get('nbr') is not None:                  # output-stationary form: one launch, fused epilogue, no atomics
+            io = lib.F16sIO()
+            io.x_split, io.x_plane = _p(feats_s), feats_s.numel() // 2
+            io.w_split, io.bias = _p(pw.w_h), _p(pw.bias)
+            if res is not None:
+                io.res = _p(res)
+            io.y = _p(out)
+            if out_s is not None:
+                io.y_split, io.y_plane = _p(out_s), out_s.numel() // 2
+            lib.check(lib.load().tt_sparse_conv_os_f16s(C.byref(d), lib.ref(io), _p(rule['nbr']), _p(rule['count']), _stream()),
+                      f'tt_sparse_conv_os_f16s[{name}]')
+        elif use_h:
             lib.check(lib.load().tt_sparse_conv_f16s(C.byref(d), _p(feats_s), C.c_longlong(feats_s.numel() // 2), _p(pw.w_h), _p(pw.bias), _p(res),
                                                      _p(rule['pairs_in']), _p(rule['pairs_out']), _p(rule['pair_count']), _p(rule['count']), _p(out),
                                                      _p(out_s), C.c_longlong(out_s.numel() // 2 if out_s is not None else 0), _stream()),

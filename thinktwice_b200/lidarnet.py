@@ -55,6 +55,7 @@ class LidarNet(nn.Module):
         self.grid = [int(v) for v in np.round((r[3:] - r[:3]) / vs)]          # (x, y, z)
         mv = self.vcfg['max_voxels']
         self.max_voxels = int(mv[1] if isinstance(mv, (list, tuple)) else mv)     # (train, eval) pair: eval
+        self.sparse_form = 'os'    # 'os': output-stationary sparse convs for the wide layers (f16s engine); 'tap': tap-major pair lists
 
     def prepare(self, pk, eng):
         self.eng = eng
@@ -89,7 +90,9 @@ class LidarNet(nn.Module):
                 self.deblocks.append(('conv', pk.conv(f'{q}{i}.0', bn=f'{q}{i}.1', eps=1e-3)))
 
     # ------------------------------------------------------------------
-    def _rulebook(self, tag, B, in_coords, in_count, cap_in, in_shape, k, s, p, subm):
+    def _rulebook(self, tag, B, in_coords, in_count, cap_in, in_shape, k, s, p, subm, form='pairs'):
+        """form: 'pairs' = tap-major (input row, output row) lists (tt_sparse_conv / _f16s); 'nbr' = per output row the input row
+        under every tap (tt_sparse_conv_os_f16s, the output-stationary form the wide layers use on the f16s engine)."""
         e = self.eng
         out_shape = in_shape if subm else tuple((in_shape[i] + 2 * p[i] - k[i]) // s[i] + 1 for i in range(3))
         cells = B * out_shape[0] * out_shape[1] * out_shape[2]
@@ -102,12 +105,16 @@ class LidarNet(nn.Module):
         kvol = k[0] * k[1] * k[2]
         ws = e.buf('sp.ws', (lib.load().tt_rulebook_workspace_bytes(C.byref(d)),), dtype=torch.uint8)
         out_coords, out_count = e.buf(f'sp.{tag}.coords', (cap_out, 4), torch.int32), e.buf(f'sp.{tag}.count', (1,), torch.int32)
-        pin, pout = e.buf(f'sp.{tag}.pin', (kvol, cap_out), torch.int32), e.buf(f'sp.{tag}.pout', (kvol, cap_out), torch.int32)
-        pcount = e.buf(f'sp.{tag}.pcount', (kvol,), torch.int32)
-        lib.call('tt_sparse_rulebook', C.byref(d), _p(in_coords), _p(in_count), _p(out_coords), _p(out_count), None, _p(pin), _p(pout),
+        pin = pout = pcount = nbr = None
+        if form == 'nbr':
+            nbr = e.buf(f'sp.{tag}.nbr', (cap_out, kvol), torch.int32)
+        else:
+            pin, pout = e.buf(f'sp.{tag}.pin', (kvol, cap_out), torch.int32), e.buf(f'sp.{tag}.pout', (kvol, cap_out), torch.int32)
+            pcount = e.buf(f'sp.{tag}.pcount', (kvol,), torch.int32)
+        lib.call('tt_sparse_rulebook', C.byref(d), _p(in_coords), _p(in_count), _p(out_coords), _p(out_count), _p(nbr), _p(pin), _p(pout),
                  _p(pcount), _p(ws))
         return dict(coords=out_coords, count=out_count, cap=cap_out, shape=out_shape, kvol=kvol, pairs_in=pin, pairs_out=pout,
-                    pair_count=pcount)
+                    pair_count=pcount, nbr=nbr)
 
     def forward(self, pts):
         """pts (B, P, 5) fp32 on the device -> [FMap (B, 84, 84, 512)] already in the Roach BEV orientation
@@ -132,7 +139,9 @@ class LidarNet(nn.Module):
 
         shape = self.me.sparse_shape
         # conv_input (SubM 5 -> 16); all SubM convs of one resolution share one rulebook (spconv indice_key)
-        rb = self._rulebook('l0', B, coords, count, cap, shape, self.k_in, (1, 1, 1), (1, 1, 1), True)
+        def form(cin):                                             # wide layers on the f16s engine: output-stationary
+            return 'nbr' if (e.split and self.sparse_form == 'os' and cin >= 32) else 'pairs'
+        rb = self._rulebook('l0', B, coords, count, cap, shape, self.k_in, (1, 1, 1), (1, 1, 1), True, form(self.stages[0][0][1].Cin))
         x, xs = e.sparse_feats('sp.l0.x', rb['cap'], self.w_in.Cout)
         e.sparse_conv(feats, self.w_in, rb, x, act=ACT_RELU, name='conv_input', out_s=xs)
         for i, st in enumerate(self.stages):
@@ -146,13 +155,13 @@ class LidarNet(nn.Module):
                     x, xs = o, os_
                 else:
                     _, wc, k, s, p = layer
-                    rd = self._rulebook(f'd{i}', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], k, s, p, False)
+                    rd = self._rulebook(f'd{i}', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], k, s, p, False, form(wc.Cin))
                     o, os_ = e.sparse_feats(f'sp.l{i + 1}.x', rd['cap'], wc.Cout)
                     e.sparse_conv(x, wc, rd, o, act=ACT_RELU, name=f'{i}.{j}.down', feats_s=xs, out_s=os_)
                     x, xs = o, os_
                     # rulebook of the SubM convs at the new resolution
-                    rb = self._rulebook(f'l{i + 1}', B, rd['coords'], rd['count'], rd['cap'], rd['shape'], (3, 3, 3), (1, 1, 1), (1, 1, 1), True)
-        ro = self._rulebook('out', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], self.k_out, (2, 1, 1), (0, 0, 0), False)
+                    rb = self._rulebook(f'l{i + 1}', B, rd['coords'], rd['count'], rd['cap'], rd['shape'], (3, 3, 3), (1, 1, 1), (1, 1, 1), True, form(wc.Cout))
+        ro = self._rulebook('out', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], self.k_out, (2, 1, 1), (0, 0, 0), False, form(self.w_out.Cin))
         o, _ = e.sparse_feats('sp.out.x', ro['cap'], self.w_out.Cout)
         x = e.sparse_conv(x, self.w_out, ro, o, act=ACT_RELU, name='conv_out', feats_s=xs)
         coords2, count2, cap2, shape2 = ro['coords'], ro['count'], ro['cap'], ro['shape']
