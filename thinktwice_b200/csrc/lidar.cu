@@ -6,6 +6,8 @@
 // coordinate and integer atomics only; the floating-point work (mean of the first `max_points` points
 // in input order, and the sparse convolutions themselves, which run through tt_conv2d's gather mode)
 // is order-deterministic.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 
 extern long long g_tt_launches;
@@ -61,13 +63,19 @@ __global__ void vox_insert_kernel(const tt_voxelize_desc d, const float* __restr
   next[p] = atomicExch(&head[slot], p);
 }
 
+// Sites are numbered in ascending (b, z, y, x) key order (the occupied keys of the table, radix-sorted): consecutive rows are
+// spatial neighbours along x, so the row gathers of the sparse convolutions walk quasi-contiguous memory and the 27 taps of a
+// tile re-read the same cache lines.  (Results do not depend on the order; locality does.)
 __global__ void vox_reduce_kernel(const tt_voxelize_desc d, const float* __restrict__ pts, const u64* __restrict__ keys,
-                                  const int* __restrict__ head, const int* __restrict__ next, int tsize,
+                                  const u64* __restrict__ skeys, const int* __restrict__ head, const int* __restrict__ next, int tsize,
                                   float* __restrict__ feats, int* __restrict__ coords, int* count) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= tsize) return;
-  const u64 key = keys[s];
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= tsize) return;
+  const u64 key = skeys[v];
   if (key == EMPTY) return;
+  if (v + 1 == tsize || skeys[v + 1] == EMPTY) *count = min(v + 1, d.cap);     // the last occupied entry knows the site count
+  if (v >= d.cap) return;
+  const int s = table_find(keys, tsize - 1, key);
   // the first max_points point ids in input order = the smallest ids of the chain
   constexpr int MAXP = 32;
   int best[MAXP];
@@ -80,8 +88,6 @@ __global__ void vox_reduce_kernel(const tt_voxelize_desc d, const float* __restr
     while (j > 0 && best[j - 1] > p) { best[j] = best[j - 1]; --j; }
     best[j] = p;
   }
-  const int v = atomicAdd(count, 1);
-  if (v >= d.cap) return;
   for (int f = 0; f < d.F; ++f) {
     float acc = 0.f;
     for (int j = 0; j < nb; ++j) acc += pts[(long long)best[j] * d.F + f];
@@ -136,10 +142,7 @@ __global__ void rb_gen_out_kernel(const tt_rulebook_desc d, const int* __restric
   const int b = coords[i * 4];
   bool fresh;
   table_insert(okeys, omask, site_key(b, o[0], o[1], o[2], d.out_shape), &fresh);
-  if (fresh) {
-    const int v = atomicAdd(out_count, 1);
-    if (v < d.cap_out) { out_coords[v * 4] = b; out_coords[v * 4 + 1] = o[0]; out_coords[v * 4 + 2] = o[1]; out_coords[v * 4 + 3] = o[2]; }
-  }
+  (void)fresh; (void)out_coords; (void)out_count;                  // the sites are emitted in key order by rb_decode_out_kernel
 }
 
 __global__ void rb_nbr_kernel(const tt_rulebook_desc d, const int* __restrict__ out_coords, const int* __restrict__ out_count,
@@ -171,7 +174,33 @@ __global__ void rb_nbr_kernel(const tt_rulebook_desc d, const int* __restrict__ 
   }
 }
 
+// output sites of a strided sparse conv = the occupied keys of `okeys`, in ascending (b, z, y, x) order (see vox_reduce_kernel)
+__global__ void rb_decode_out_kernel(const tt_rulebook_desc d, const u64* __restrict__ skeys, int tsize, int* __restrict__ out_coords,
+                                     int* out_count) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= tsize) return;
+  u64 k = skeys[v];
+  if (k == EMPTY) return;
+  if (v + 1 == tsize || skeys[v + 1] == EMPTY) *out_count = min(v + 1, d.cap_out);
+  if (v >= d.cap_out) return;
+  const int x = k % d.out_shape[2]; k /= d.out_shape[2];
+  const int y = k % d.out_shape[1]; k /= d.out_shape[1];
+  const int z = k % d.out_shape[0]; k /= d.out_shape[0];
+  out_coords[v * 4] = (int)k; out_coords[v * 4 + 1] = z; out_coords[v * 4 + 2] = y; out_coords[v * 4 + 3] = x;
+}
+
 __global__ void clamp_count_kernel(int* count, int cap) { if (*count > cap) *count = cap; }
+
+// radix sort of a hash table's key array (EMPTY = all ones sorts last); only the bits a valid key can occupy (+1) are sorted
+size_t sort_temp_bytes(int T) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const u64*)nullptr, (u64*)nullptr, T, 0, 64);
+  return bytes;
+}
+int key_bits(unsigned long long cells) { int b = 1; while (b < 63 && (1ull << b) <= cells) ++b; return b + 1 > 64 ? 64 : b + 1; }
+bool sort_keys(const u64* keys, u64* sorted, int T, unsigned long long cells, void* temp, size_t temp_bytes, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys, sorted, T, 0, key_bits(cells), st) == cudaSuccess;
+}
 
 __global__ void sparse_to_bev_kernel(const float* __restrict__ feats, const int* __restrict__ coords,
                                      const int* __restrict__ count, int cap, int C, int D, int H, int W, int at,
@@ -196,7 +225,7 @@ extern "C" {
 size_t tt_voxelize_workspace_bytes(const tt_voxelize_desc* d) {
   if (!d) return 0;
   const size_t T = pow2_at_least(2ll * d->B * d->P);
-  return al(T * 8) + al(T * 4) + al((size_t)d->B * d->P * 4);
+  return al(T * 8) + al(T * 4) + al((size_t)d->B * d->P * 4) + al(T * 8) + al(sort_temp_bytes((int)T));
 }
 
 int tt_voxelize_mean(const tt_voxelize_desc* d, const float* points, float* feats, int* coords, int* count,
@@ -210,6 +239,8 @@ int tt_voxelize_mean(const tt_voxelize_desc* d, const float* points, float* feat
   u64* keys = (u64*)ws;
   int* head = (int*)(ws + al((size_t)T * 8));
   int* next = (int*)(ws + al((size_t)T * 8) + al((size_t)T * 4));
+  u64* skeys = (u64*)(ws + al((size_t)T * 8) + al((size_t)T * 4) + al((size_t)d->B * d->P * 4));
+  void* stemp = ws + al((size_t)T * 8) + al((size_t)T * 4) + al((size_t)d->B * d->P * 4) + al((size_t)T * 8);
   if (cudaMemsetAsync(keys, 0xFF, (size_t)T * 8, st) != cudaSuccess || cudaMemsetAsync(head, 0xFF, (size_t)T * 4, st) != cudaSuccess ||
       cudaMemsetAsync(count, 0, 4, st) != cudaSuccess) {
     tt_set_error("tt_voxelize_mean: memset failed");
@@ -219,10 +250,13 @@ int tt_voxelize_mean(const tt_voxelize_desc* d, const float* points, float* feat
   if (np > 0) {
     vox_insert_kernel<<<tt_cdiv(np, 256), 256, 0, st>>>(*d, points, keys, head, next, T - 1);
     TT_LAUNCHED("tt_voxelize_mean(insert)");
-    vox_reduce_kernel<<<tt_cdiv(T, 256), 256, 0, st>>>(*d, points, keys, head, next, T, feats, coords, count);
+    if (!sort_keys(keys, skeys, T, (unsigned long long)d->B * d->grid[0] * d->grid[1] * d->grid[2], stemp, sort_temp_bytes(T), st)) {
+      tt_set_error("tt_voxelize_mean: radix sort failed");
+      return TT_ERR_CUDA;
+    }
+    ++g_tt_launches;
+    vox_reduce_kernel<<<tt_cdiv(T, 256), 256, 0, st>>>(*d, points, keys, skeys, head, next, T, feats, coords, count);
     TT_LAUNCHED("tt_voxelize_mean(reduce)");
-    clamp_count_kernel<<<1, 1, 0, st>>>(count, d->cap);
-    TT_LAUNCHED("tt_voxelize_mean(clamp)");
   }
   return TT_OK;
 }
@@ -230,7 +264,7 @@ int tt_voxelize_mean(const tt_voxelize_desc* d, const float* points, float* feat
 size_t tt_rulebook_workspace_bytes(const tt_rulebook_desc* d) {
   if (!d) return 0;
   const size_t T = d->table_size;
-  return al(T * 8) + al(T * 4) + (d->subm ? 0 : al(T * 8));
+  return al(T * 8) + al(T * 4) + (d->subm ? 0 : al(T * 8) + al(T * 8) + al(sort_temp_bytes((int)T)));
 }
 
 int tt_sparse_rulebook(const tt_rulebook_desc* d, const int* in_coords, const int* in_count, int* out_coords,
@@ -263,8 +297,15 @@ int tt_sparse_rulebook(const tt_rulebook_desc* d, const int* in_coords, const in
     rb_gen_out_kernel<<<tt_cdiv((long long)d->cap_in * kvol, 256), 256, 0, st>>>(*d, in_coords, in_count, okeys, T - 1,
                                                                                  out_coords, out_count);
     TT_LAUNCHED("tt_sparse_rulebook(gen_out)");
-    clamp_count_kernel<<<1, 1, 0, st>>>(out_count, d->cap_out);
-    TT_LAUNCHED("tt_sparse_rulebook(clamp)");
+    u64* sokeys = okeys + al((size_t)T * 8) / 8;
+    void* stemp = sokeys + al((size_t)T * 8) / 8;
+    if (!sort_keys(okeys, sokeys, T, (unsigned long long)d->B * d->out_shape[0] * d->out_shape[1] * d->out_shape[2], stemp, sort_temp_bytes(T), st)) {
+      tt_set_error("tt_sparse_rulebook: radix sort failed");
+      return TT_ERR_CUDA;
+    }
+    ++g_tt_launches;
+    rb_decode_out_kernel<<<tt_cdiv(T, 256), 256, 0, st>>>(*d, sokeys, T, out_coords, out_count);
+    TT_LAUNCHED("tt_sparse_rulebook(decode_out)");
   }
   if (pair_count && cudaMemsetAsync(pair_count, 0, (size_t)kvol * 4, st) != cudaSuccess) { tt_set_error("tt_sparse_rulebook: memset failed"); return TT_ERR_CUDA; }
   rb_nbr_kernel<<<tt_cdiv((long long)d->cap_out * kvol, 256), 256, 0, st>>>(*d, out_coords, out_count, keys, vals, T - 1, nbr,
