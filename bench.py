@@ -353,7 +353,7 @@ def main():
                           'algorithmic_flops_per_step': conv_flops,
                           'frac_lower_bound': conv_flops / (ms / args.steps * 1e-3) / 1e12 / tensor_peak,
                           'lower_bound_note': 'family FLOPs / the WHOLE timed (graph-replayed) step: what the family achieves at least'},
-                segments_ms_serial_eager=segments,
+                segments_ms_serial_eager=segments, hbm_peak_allocated_gb=round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
                 checks={'timed_mode_vs_eager_pred_wp_relerr': parity, 'f16s_saturated_operands': saturated})
     if lat is not None:
         line['latency_b1'] = {'ms_per_frame': lat, 'frames_per_s': 1000.0 / lat,

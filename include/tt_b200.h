@@ -304,8 +304,10 @@ typedef struct {
   int BN, rows_cap, heads, levels, points, dh; /* 8 heads, 4 levels, 8 points, 32 */
   int lvl_h[4], lvl_w[4], lvl_start[4];
   int num_keys;
+  int value_ld, value_coff;      /* floats per key row of `value` (0 = heads*dh) and first channel: several layers' value projections
+                                  * computed by ONE convolution share a buffer */
 } tt_msda_desc;
-/* value [BN][num_keys][heads*dh]; off [BN*cap][heads*levels*points*2]; logits [BN*cap][heads*levels*points];
+/* value [BN][num_keys][value_ld] (channels value_coff .. value_coff + heads*dh); off [BN*cap][heads*levels*points*2]; logits [BN*cap][heads*levels*points];
  * ref [BN*cap][2]; out [BN*cap][heads*dh].  Softmax over levels*points is fused. */
 int tt_msda_forward(const tt_msda_desc* d, const float* value, const float* off, const float* logits, const float* ref,
                     const int* max_len, float* out, tt_stream_t stream);

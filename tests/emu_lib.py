@@ -638,7 +638,8 @@ class Emu:
         self.launches += 1
         BN, cap, Hh, L, P, dh = d.BN, d.rows_cap, d.heads, d.levels, d.points, d.dh
         shapes = [(d.lvl_h[l], d.lvl_w[l]) for l in range(L)]
-        v = value.flat()[:BN * d.num_keys * Hh * dh].view(BN, d.num_keys, Hh, dh)
+        VL = d.value_ld or Hh * dh
+        v = value.flat()[:BN * d.num_keys * VL].view(BN, d.num_keys, VL)[..., d.value_coff:d.value_coff + Hh * dh].reshape(BN, d.num_keys, Hh, dh)
         o = off.flat()[:BN * cap * Hh * L * P * 2].view(BN, cap, Hh, L, P, 2)
         lg = logits.flat()[:BN * cap * Hh * L * P].view(BN, cap, Hh, L * P)
         r = ref.flat()[:BN * cap * 2].view(BN, cap, 1, 1, 1, 2)

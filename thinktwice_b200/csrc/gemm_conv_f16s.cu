@@ -124,6 +124,7 @@ struct HArgs {
   const int* nbr;        // output-stationary: [cap_rows][kvol] input row under each tap of an output row, -1 = none
   const int* out_count;  // output-stationary: number of output rows (device scalar)
   int cap_rows;
+  int tps;               // output-stationary: taps per 64-half K slab (2 when Cin == 32, else 1)
   int splits, k_per;     // split-K: K stages per split
 };
 
@@ -161,7 +162,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool GATHER = GM != 0;
   const int taps = GM == 2 ? p.kvol : d.KH * d.KW;
-  const int k_iters = taps * p.n_slabs;
+  // output-stationary with Cin = 32: a 64-half K slab holds TWO taps (p.tps = 2), so no half of a slab is padding
+  const int k_iters = (GM == 2 && p.tps == 2) ? (p.kvol + 1) / 2 : taps * p.n_slabs;
   const int os_rows = GM == 2 ? min(*p.out_count, p.cap_rows) : 0;     // output-stationary: rows that exist (device count)
   // PAIR: CTA pairs (cluster of 2) walk two M tiles of the same N tile in lockstep and multicast weight halves to each other;
   // !PAIR: every CTA is on its own (loads the whole weight slab itself, no cross-CTA barriers) — measured alternative
@@ -250,6 +252,39 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       for (int it = kb; it < ke; ++it, ++ig) {
         const int s = ig % STAGES;
+        if (GM == 2 && p.tps == 2) {
+          // ---- two taps per K slab (Cin = 32): chunks 0..3 of a row come from the neighbour under tap 2 it, chunks 4..7 from tap 2 it + 1
+          int ra[4], rb[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = mt * BM + lane + 32 * i;
+            const int* nb = p.nbr + (long long)m * p.kvol + 2 * it;
+            ra[i] = m < count ? __ldg(nb) : -1;
+            rb[i] = (m < count && 2 * it + 1 < p.kvol) ? __ldg(nb + 1) : -1;
+          }
+          mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          if (lane == 0) {
+            mbar_expect_tx(&full[s], txb);
+            load_weights(st, &full[s], it * KE, 0, n0);              // weights viewed as [Cout][kvol * 32]: K runs across the taps
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            const uint32_t dst = smem_u32(st) + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int row = j < 4 ? ra[i] : rb[i];
+              const bool ok = row >= 0;
+              const __half* src = p.gx + (long long)max(row, 0) * p.gx_ld + (j & 3) * 8;
+              const uint32_t o = (uint32_t)((j ^ (r & 7)) << 4);
+              cp_async16(dst + o, ok ? (const void*)src : (const void*)p.gx, ok ? 16 : 0);
+              cp_async16(dst + A_BYTES + o, ok ? (const void*)(src + p.gx_plane) : (const void*)p.gx, ok ? 16 : 0);
+            }
+          }
+          cp_async_arrive_noinc(&full[s]);
+          continue;
+        }
         const int ktap = GM == 2 ? it / p.n_slabs : tap;            // output-stationary: the K walk visits every tap
         const int slab = GM == 2 ? it - ktap * p.n_slabs : it;
         if (GM == 2 && (slab == 0 || it == kb)) {
@@ -401,10 +436,10 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int nimg, oh, ow;
         long long rrow;
         if (p.flat) {
-          const long long pix = (long long)mt * BM + r;
+          const int pix = mt * BM + r;                       // (the host checked N * OH * OW < 2^31: 32-bit index math)
           valid = real_tile && pix < p.total_pix;
-          nimg = (int)(pix / HWo);
-          const int rem = (int)(pix - (long long)nimg * HWo);
+          nimg = pix / HWo;
+          const int rem = pix - nimg * HWo;
           oh = rem / d.OW; ow = rem - oh * d.OW;
           rrow = pix;
         } else {
@@ -470,41 +505,53 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int sub = lane >> 2, cl = (lane & 3) * 4;
+      // the 4 rows this lane stores (row groups of 8) are the same for every column slab: their table entries are read ONCE
+      // per tile into registers (the profile showed the per-slab table reloads and the residual round trips as the epilogue's
+      // long-scoreboard stalls on the short-K layers, where the epilogue sets the pace: profiles/r2_summary.md)
+      int fl[4];
+      long long yo[4], o1[4], o2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = q * 32 + i * 8 + sub;
+        fl[i] = row_flag[rr];
+        yo[i] = row_y[rr];
+        o1[i] = row_r1[rr];
+        o2[i] = row_r2[rr];
+      }
 #pragma unroll
       for (int sl = 0; sl < HN / SLAB; ++sl) {
+        const int col = n0 + sl * SLAB + cl;
+        const bool live = col < d.Cout && !(p.dbg & 1);
+        // residual / bias loads of this slab are issued BEFORE the shared-memory transposition so that the two latencies overlap
+        float4 ra[4], rb[4];
+        float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          rb[i] = ra[i];
+          if (live && (fl[i] & 1)) {
+            if (p.res) ra[i] = *reinterpret_cast<const float4*>(p.res + o1[i] + col);
+            else if (p.res_s) ra[i] = load_split4(p.res_s + o1[i] + col, p.res_plane);
+            if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + o2[i] + col);
+            else if (p.res2_s) rb[i] = load_split4(p.res2_s + o2[i] + col, p.res2_plane);
+          }
+        }
+        if (live && p.bias && !d.bias_n_mod) bv0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));   // one bias vector: once per slab
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < SLAB; j += 4)
           *reinterpret_cast<float4*>(&tile[lane * PITCH + j]) =
               make_float4(sum[sl * SLAB + j], sum[sl * SLAB + j + 1], sum[sl * SLAB + j + 2], sum[sl * SLAB + j + 3]);
         __syncwarp();
-        const int col = n0 + sl * SLAB + cl;
-        if (col < d.Cout && !(p.dbg & 1)) {
-          float4 acc4[4], ra[4], rb[4];
-          int fl[4];
-          long long yo[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int lr = i * 8 + sub, rr = q * 32 + lr;
-            fl[i] = row_flag[rr];
-            yo[i] = row_y[rr];
-            acc4[i] = *reinterpret_cast<const float4*>(&tile[lr * PITCH + cl]);
-            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rb[i] = ra[i];
-            if (fl[i] & 1) {
-              if (p.res) ra[i] = *reinterpret_cast<const float4*>(p.res + row_r1[rr] + col);
-              else if (p.res_s) ra[i] = load_split4(p.res_s + row_r1[rr] + col, p.res_plane);
-              if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + row_r2[rr] + col);
-              else if (p.res2_s) rb[i] = load_split4(p.res2_s + row_r2[rr] + col, p.res2_plane);
-            }
-          }
+        if (live) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (!(fl[i] & 1)) continue;
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (d.bias_n_mod ? (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout : 0) + col));
-            float4 o = make_float4(acc4[i].x + bv.x + ra[i].x + rb[i].x, acc4[i].y + bv.y + ra[i].y + rb[i].y,
-                                   acc4[i].z + bv.z + ra[i].z + rb[i].z, acc4[i].w + bv.w + ra[i].w + rb[i].w);
+            const float4 acc4 = *reinterpret_cast<const float4*>(&tile[(i * 8 + sub) * PITCH + cl]);
+            float4 bv = bv0;
+            if (p.bias && d.bias_n_mod) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout + col));
+            float4 o = make_float4(acc4.x + bv.x + ra[i].x + rb[i].x, acc4.y + bv.y + ra[i].y + rb[i].y,
+                                   acc4.z + bv.z + ra[i].z + rb[i].z, acc4.w + bv.w + ra[i].w + rb[i].w);
             const long long eo = yo[i] + col;
             if (GM == 1 || p.splits > 1) {                     // taps / K splits race on an output row: red.add (fp32 only)
               tt_red_add_v4(p.y + eo, o.x, o.y, o.z, o.w);
@@ -667,8 +714,9 @@ cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CU
   return pair ? launch_f16s_v<BN, STAGES, GATHER, true>(cfg, ma, mb, a) : launch_f16s_v<BN, STAGES, GATHER, false>(cfg, ma, mb, a);
 }
 
-bool encode_weights(CUtensorMap* mb, const void* w_split, int Cin, int taps, int Cout, int BN) {
-  const int cin_pad = (Cin + 7) & ~7;
+bool encode_weights(CUtensorMap* mb, const void* w_split, int Cin, int taps, int Cout, int BN, bool flat_k = false) {
+  int cin_pad = (Cin + 7) & ~7;
+  if (flat_k) { cin_pad *= taps; taps = 1; }                     // K = tap * Cin + c as ONE dimension (taps are contiguous per Cout row)
   cuuint64_t dims[4] = {(cuuint64_t)cin_pad, (cuuint64_t)taps, (cuuint64_t)Cout, 2};
   cuuint64_t str[3] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)taps * cin_pad * 2, (cuuint64_t)Cout * taps * cin_pad * 2};
   cuuint32_t box[4] = {KE, 1, (cuuint32_t)(BN / 2), 1};          // each CTA of a pair loads (and multicasts) half of a plane's slab
@@ -761,6 +809,10 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
   a.ys = static_cast<__half*>(y_split); a.ys_plane = y_plane;
   a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;   // 2 stages = K 128 = 8 truncating accumulations per chunk
   a.n_slabs = (d->Cin + KE - 1) / KE;
+  if ((long long)d->N * d->OH * d->OW >= (1ll << 31) - BM || npix_in >= (1ll << 31) - BM) {
+    tt_set_error("tt_conv2d_f16s: more than 2^31 pixels");
+    return TT_ERR_UNSUPPORTED;
+  }
   a.total_pix = d->N * d->OH * d->OW;
   a.flat = (taps == 1 && d->pad == 0 && d->stride == 1 && xhs == (long long)d->W * d->x_ld && xns == (long long)d->H * xhs) ? 1 : 0;
   CUtensorMap ma, mb;
@@ -930,11 +982,12 @@ int tt_sparse_conv_os_f16s(const tt_sparse_conv_desc* d, const tt_f16s_io* io, c
   a.dbg = g_tt_debug & 0xFF;
   a.gx = static_cast<const __half*>(io->x_split); a.gx_plane = io->x_plane; a.gx_ld = d->in_ld;
   a.kvol = d->kvol; a.nbr = nbr; a.out_count = out_count; a.cap_rows = d->cap_out;
-  a.splits = 1; a.k_per = d->kvol * a.n_slabs;
+  a.tps = (d->Cin == 32 && !(g_tt_debug & 0x200000)) ? 2 : 1;
+  a.splits = 1; a.k_per = a.tps == 2 ? (d->kvol + 1) / 2 : d->kvol * a.n_slabs;
   const int BN = d->Cout > 64 ? 128 : 64;
   a.n_tiles = tt_cdiv(d->Cout, BN);
   CUtensorMap mb;
-  if (!encode_weights(&mb, io->w_split, d->Cin, d->kvol, d->Cout, BN)) return TT_ERR_CUDA;
+  if (!encode_weights(&mb, io->w_split, d->Cin, d->kvol, d->Cout, BN, a.tps == 2)) return TT_ERR_CUDA;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(NTHREADS);
   cfg.stream = (cudaStream_t)stream;

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256) msda_kernel(const tt_msda_desc d, const f
   const float ox = lane < S ? off[(row * d.heads + head) * S * 2 + lane * 2] : 0.f;
   const float oy = lane < S ? off[(row * d.heads + head) * S * 2 + lane * 2 + 1] : 0.f;
   const float rx = ref[row * 2], ry = ref[row * 2 + 1];
-  const float* vb = value + (long long)bn * d.num_keys * E + head * d.dh + lane;
+  const int VL = d.value_ld ? d.value_ld : E;               // key-row pitch of the value buffer
+  const float* vb = value + (long long)bn * d.num_keys * VL + d.value_coff + head * d.dh + lane;
   float acc = 0.f;
   for (int s = 0; s < S; ++s) {
     const int l = s / d.points;
@@ -154,15 +155,15 @@ __global__ void __launch_bounds__(256) msda_kernel(const tt_msda_desc d, const f
     if (!(x > -1.f && y > -1.f && x < (float)W && y < (float)H)) continue;
     const int x0 = (int)floorf(x), y0 = (int)floorf(y);
     const float lx = x - x0, ly = y - y0;
-    const float* v = vb + (long long)d.lvl_start[l] * E;
+    const float* v = vb + (long long)d.lvl_start[l] * VL;
     float sv = 0.f;
     if (y0 >= 0) {
-      if (x0 >= 0) sv += (1.f - ly) * (1.f - lx) * __ldg(v + ((long long)y0 * W + x0) * E);
-      if (x0 + 1 < W) sv += (1.f - ly) * lx * __ldg(v + ((long long)y0 * W + x0 + 1) * E);
+      if (x0 >= 0) sv += (1.f - ly) * (1.f - lx) * __ldg(v + ((long long)y0 * W + x0) * VL);
+      if (x0 + 1 < W) sv += (1.f - ly) * lx * __ldg(v + ((long long)y0 * W + x0 + 1) * VL);
     }
     if (y0 + 1 < H) {
-      if (x0 >= 0) sv += ly * (1.f - lx) * __ldg(v + ((long long)(y0 + 1) * W + x0) * E);
-      if (x0 + 1 < W) sv += ly * lx * __ldg(v + ((long long)(y0 + 1) * W + x0 + 1) * E);
+      if (x0 >= 0) sv += ly * (1.f - lx) * __ldg(v + ((long long)(y0 + 1) * W + x0) * VL);
+      if (x0 + 1 < W) sv += ly * lx * __ldg(v + ((long long)(y0 + 1) * W + x0 + 1) * VL);
     }
     acc = fmaf(w_s, sv, acc);
   }

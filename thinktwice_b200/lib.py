@@ -69,7 +69,8 @@ class LookDesc(C.Structure):
 
 class MsdaDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ('BN', 'rows_cap', 'heads', 'levels', 'points', 'dh')] + \
-               [('lvl_h', C.c_int * 4), ('lvl_w', C.c_int * 4), ('lvl_start', C.c_int * 4), ('num_keys', C.c_int)]
+               [('lvl_h', C.c_int * 4), ('lvl_w', C.c_int * 4), ('lvl_start', C.c_int * 4), ('num_keys', C.c_int), ('value_ld', C.c_int),
+                ('value_coff', C.c_int)]
 
 
 _lib = None

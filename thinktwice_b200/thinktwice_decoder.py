@@ -91,11 +91,12 @@ class ThinkTwiceDecoder(nn.Module):
             L['q3'] = pk.linear(c + 'query_linear.3')
             L['off'] = pk.linear(c + 'deformable_attention.sampling_offsets')
             L['aw'] = pk.linear(c + 'deformable_attention.attention_weights')
-            # value_proj(x + cams_embeds[cam] + level_embeds[lvl]) = W x + (W (e_cam + e_lvl) + b): one bias per (cam, lvl)
+            # value_proj(x + cams_embeds[cam] + level_embeds[lvl]) = W x + (W (e_cam + e_lvl) + b): one bias per (cam, lvl).
+            # The K layers' value projections depend only on the FPN maps, not on the cascade: they are packed as ONE
+            # 256 -> K*256 projection per level (self.value_all, built after this loop) and run once, ahead of the cascade.
             Wv, bv = pk.sd[c + 'deformable_attention.value_proj.weight'].double(), pk.sd[c + 'deformable_attention.value_proj.bias'].double()
-            L['value'] = [pk.linear(c + 'deformable_attention.value_proj',
-                                    bias=torch.stack([bv + Wv @ (cams[cam] + lvls[l]) for cam in range(4)]).float().reshape(-1))
-                          for l in range(4)]                     # per level: bias table [4 cams][256] (bias_n_mod = 4)
+            L['_value_w'] = Wv
+            L['_value_b'] = [torch.stack([bv + Wv @ (cams[cam] + lvls[l]) for cam in range(4)]) for l in range(4)]    # [level] -> (4 cams, 256)
             L['ffn_ln'] = (pk.vec(c + 'ffn.norm.weight'), pk.vec(c + 'ffn.norm.bias'))
             L['ffn1'], L['ffn2'] = pk.linear(c + 'ffn.w_1'), pk.linear(c + 'ffn.w_2')
             L['op_ln'] = (pk.vec(c + 'output_proj.0.weight'), pk.vec(c + 'output_proj.0.bias'))
@@ -107,6 +108,12 @@ class ThinkTwiceDecoder(nn.Module):
             L['bev_up'] = (pk.conv(q + 'BEV_feat_update_module.0'), pk.conv(q + 'BEV_feat_update_module.2'))
             L['flat_up'] = (pk.linear(q + 'flattened_BEV_feat_update_module.0'), pk.linear(q + 'flattened_BEV_feat_update_module.2'))
             self.layers.append(L)
+        Wcat = torch.cat([L['_value_w'] for L in self.layers], 0)              # (K*256, 256): layer k owns output channels [256k, 256k+256)
+        self.value_all = [pk.linear(p + 'value_proj_all', weight=Wcat,
+                                    bias=torch.cat([L['_value_b'][l] for L in self.layers], 1).float().reshape(-1))
+                          for l in range(4)]                            # per level: bias table [4 cams][K*256] (bias_n_mod = 4)
+        for L in self.layers:
+            del L['_value_w'], L['_value_b']
 
     def stage(self, lidar2img, ida):
         """host half: upload the (B, 4, 4, 4) projection matrices the Look module needs."""
@@ -146,6 +153,17 @@ class ThinkTwiceDecoder(nn.Module):
             e.conv(d1, L['conv_decoder'][1], out=out_t, name='gru.d', pad=1, y_nstride=T * HW * Cs)
         return fut
 
+    def _values(self, mlvl, meta):
+        """value_proj of every decoder layer over all keys of every (camera, level): ONE 256 -> K*256 projection per FPN level
+        (msda:474 per layer in the reference: the FPN maps are read once instead of K times, 4 launches instead of 4K)."""
+        e = self.eng
+        B, cams, nk, KC = meta['B'], 4, meta['num_keys'], self.K * 256
+        value = e.buf('look.value_all', (B * cams, nk, KC))
+        for l, m in enumerate(mlvl):
+            out = FMap(value, B * cams, m.H, m.W, KC, KC, meta['lvl_start'][l] * KC)
+            e.conv(m, self.value_all[l], out=out, name=f'look.value{l}', y_nstride=nk * KC, bias_n_mod=cams)
+        return value
+
     def _look(self, L, k, wp, ctrl_sp, meas, flat, mlvl, meta):
         """LookModule.forward (thinktwice_decoder.py:154-187), image branch."""
         e = self.eng
@@ -165,16 +183,15 @@ class ThinkTwiceDecoder(nn.Module):
         q = e.layernorm(rows, *L['q_ln'], name='look.q_ln', out_ld=1544)
         q = e.linear(q.view(q.N, 1, 1, 1544), L['q1'], name='look.q1', act=ACT_GELU)
         q = e.linear(q, L['q3'], name='look.q', act=ACT_GELU)
-        # value_proj over all keys of every (cam, level) with the embedding folded into the bias (msda:474)
+        # value_proj (msda:474): computed for all layers at once before the cascade (_values); layer k reads its channel block
         nk = meta['num_keys']
-        value = e.buf('look.value', (B * cams, nk, 256))
-        for l, m in enumerate(mlvl):                                 # one launch per level over all B*cams images
-            out = FMap(value, B * cams, m.H, m.W, 256, 256, meta['lvl_start'][l] * 256)
-            e.conv(m, L['value'][l], out=out, name=f'look.value{l}', y_nstride=nk * 256, bias_n_mod=cams)
+        value = meta['value_all']
         off = e.linear(q, L['off'], name='look.off')
         aw = e.linear(q, L['aw'], name='look.aw')
         att = e.fmap('look.att', B * cams * cap, 1, 1, 256)
-        lib.call('tt_msda_forward', C.byref(meta['msda_desc']), _p(value), _p(off.t), _p(aw.t), _p(ref_re), _p(max_len), _p(att.t))
+        md = meta['msda_desc']
+        md.value_ld, md.value_coff = self.K * 256, k * 256
+        lib.call('tt_msda_forward', C.byref(md), _p(value), _p(off.t), _p(aw.t), _p(ref_re), _p(max_len), _p(att.t))
         # PositionwiseFeedForward (msda:197-214)
         h = e.layernorm(att, *L['ffn_ln'], name='look.ffn_ln')
         h = e.linear(h, L['ffn1'], name='look.ffn1', act=ACT_GELU)
@@ -216,6 +233,7 @@ class ThinkTwiceDecoder(nn.Module):
         # ---- Look-module inputs (thinktwice_decoder.py:442-450)
         mlvl = [e.conv(fpn[i], w['fpn_linear'][i], name=f'dec.mlvl{i}') for i in range(4)]
         meta = self._look_meta(B, mlvl)
+        meta['value_all'] = self._values(mlvl, meta)
 
         cur_bev, cur_flat = bev, flat
         s_bev, s_flat, s_fut = [], [], []

@@ -10,5 +10,6 @@ tail -3 gpurun_out/r2_ncu_ops_b$B.log | cut -c1-300
 python tools/ncu_summary.py /tmp/r2_ops_b$B.ncu-rep gpurun_out/r2_kernels_b$B
 ncu -i /tmp/r2_ops_b$B.ncu-rep --page raw --csv > gpurun_out/r2_ops_b${B}_raw.csv 2>/dev/null
 # the dominant tensor-core kernel with source correlation (3 launches of the 3x3 256->256 @112x224 layer)
-SHAPES=4 IMPLS=4 ncu --set full --clock-control none --import-source on -k regex:conv_f16s -s 10 -c 3 -f -o gpurun_out/r2_f16s_3x3 python tools/conv_bench.py 0 > gpurun_out/r2_ncu_f16s_3x3.log 2>&1
+SHAPES=0,4 IMPLS=4 NMUL=4 ncu --set full --clock-control none --import-source on -k regex:conv_f16s -s 22 -c 1 -f -o gpurun_out/r2_f16s_1x1 python tools/conv_bench.py 0 > gpurun_out/r2_ncu_f16s_1x1.log 2>&1
+SHAPES=4 IMPLS=4 NMUL=4 ncu --set full --clock-control none --import-source on -k regex:conv_f16s -s 22 -c 1 -f -o gpurun_out/r2_f16s_3x3 python tools/conv_bench.py 0 > gpurun_out/r2_ncu_f16s_3x3.log 2>&1
 ls -la gpurun_out | tail -8
