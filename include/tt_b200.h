@@ -149,6 +149,11 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
 /* fp32 rows [rows][x_ld] (first `cols` columns) -> split planes [2][rows][y_ld]; only the first *row_count rows when given */
 int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plane, long long y_ld, long long rows, int cols,
                  const int* row_count, tt_stream_t stream);
+/* NCHW fp32 images (C <= 8) -> zero-bordered channels-last split planes [2][N][out_H][out_W][8 halves] at pixel offset (top, left): the
+ * input layout of the row-packed stem convolution on the f16s engine (replaces tt_nchw_to_nhwc_padded + tt_split_f16; the border
+ * is never written: zero the buffer once). */
+int tt_image_to_split8(const float* x, void* y_split, long long y_plane, int N, int C, int H, int W, int out_H, int out_W, int top,
+                       int left, tt_stream_t stream);
 /* split planes -> fp32 rows (hi + lo' / 2048): for a non-convolution kernel that must read a tensor stored as planes only */
 int tt_merge_f16(const void* x_split, long long x_plane, long long x_ld, float* y, long long y_ld, long long rows, int cols,
                  tt_stream_t stream);

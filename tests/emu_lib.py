@@ -198,6 +198,17 @@ class Emu:
         torch.as_strided(Ptr(y_split.t, y_split.off + y_plane).flat(), (n, cols), (y_ld, 1)).copy_(lo)
         return 0
 
+    def tt_image_to_split8(self, x, y_split, y_plane, N, Cc, H, W, out_H, out_W, top, left, stream):
+        self.launches += 1
+        y_plane = _v(y_plane)
+        img = x.flat()[:N * Cc * H * W].view(N, Cc, H, W).permute(0, 2, 3, 1)
+        hi, lo = _split_f16(img)
+        for plane, val in ((0, hi), (y_plane, lo)):
+            dst = Ptr(y_split.t, y_split.off + plane).flat()[:N * out_H * out_W * 8].view(N, out_H, out_W, 8)
+            dst[:, top:top + H, left:left + W, :Cc] = val
+            dst[:, top:top + H, left:left + W, Cc:] = 0
+        return 0
+
     def tt_merge_f16(self, x_split, x_plane, x_ld, y, y_ld, rows, cols, stream):
         self.launches += 1
         x_plane, x_ld, y_ld, rows = _v(x_plane), _v(x_ld), _v(y_ld), _v(rows)

@@ -165,11 +165,14 @@ def test_f16s_rowpacked_stem_conv_matches_fp64():
     w = torch.randn(Cout, 3, 7, 7, generator=gen) * 0.08
     eng = engine()
     pw = Packer({'c.weight': w}, torch.device('cuda:0'), tc_mode=IMPL).conv_rowpacked('c', cpad=8, kslab=64)
-    pb = eng.nchw_to_nhwc_padded(x.cuda(), 'h.img', 4, 3, 3, 3, 5)
     Wp = W + 8
     rows = N * (H + 6) * Wp
     pbs = eng.buf('h.img#s8', (2, rows * 8), torch.float16, zero=True)
-    lib.call('tt_split_f16', _p(pb), C.c_longlong(4), _p(pbs), C.c_longlong(rows * 8), C.c_longlong(8), C.c_longlong(rows), 4, None)
+    xd = x.cuda().contiguous()
+    lib.call('tt_image_to_split8', _p(xd), _p(pbs), C.c_longlong(rows * 8), N, 3, H, W, H + 6, Wp, 3, 3)
+    img = (pbs[0].float() + pbs[1].float() / 2048.0).view(N, H + 6, Wp, 8)
+    assert float((img[:, 3:3 + H, 3:3 + W, :3] - xd.permute(0, 2, 3, 1)).abs().max()) < 1e-6 * float(xd.abs().max())
+    assert float(img[:, :3].abs().max()) == 0 and float(img[:, :, :3].abs().max()) == 0 and float(img[..., 3:].abs().max()) == 0
     n0 = lib.launch_count()
     y = eng.conv(FMap(None, N, H + 6, W, 64, ld=8, s=pbs), pw, name='h.stem', stride=2, act=1, x_hstride=Wp * 8, x_nstride=(H + 6) * Wp * 8)
     torch.cuda.synchronize()

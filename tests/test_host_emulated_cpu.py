@@ -49,6 +49,20 @@ def test_plumbing_forward_through_the_emulated_abi_matches_the_oracle(emulated, 
     assert rel(cam['depth'].nchw().softmax(1), keep['cam_keep']['depth_prob']) < 1e-3
 
 
+def test_value_proj_layer_by_layer_path_matches_the_merged_one(emulated):
+    """the K layers' value_proj run as ONE projection per FPN level when the K-fold value tensor fits the budget (latency configs),
+    layer by layer into one reused buffer otherwise (B = 32): both against the oracle."""
+    from thinktwice_b200.config import PLUMBING_CONFIG
+    o, m, batch = _pair(PLUMBING_CONFIG, 2, 900, 5, 4)
+    with torch.no_grad():
+        ref = o.forward_inference(batch)
+    merged = {k: m.forward_inference(batch)[k].clone() for k in ('pred_wp', 'mu_branches')}
+    m.decoder.value_all_budget = 0
+    layered = m.forward_inference(batch)
+    for k, v in merged.items():
+        assert rel(v, ref[k]) < 5e-4 and rel(layered[k], ref[k]) < 5e-4, k
+
+
 def test_full_thinktwice_config_through_the_emulated_abi_matches_the_oracle(emulated):
     """the bench workload (thinktwice.py: 4 cams x 2 sweeps 448x896, 40k LiDAR points, K = 5, B = 1) with the tensor-core weight
     layouts: ~1000 emulated launches, ~70 s of CPU."""

@@ -653,6 +653,27 @@ __global__ void merge_rows_kernel(const __half* __restrict__ xs, long long xs_pl
   }
 }
 
+// camera images NCHW fp32 (C <= 8) -> zero-bordered channels-last split planes with 8 halves per pixel: the layout the row-packed
+// stem convolution reads (one 7-pixel tap row = 56 halves of a 64-half K slab).  One thread per pixel: coalesced plane reads,
+// one 16-byte store per plane.
+__global__ void image_to_split8_kernel(const float* __restrict__ x, __half* __restrict__ ys, long long ys_plane, int C, int H, int W,
+                                       int out_H, int out_W, int top, int left, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long t = i / W;
+    const int h = (int)(t % H), n = (int)(t / H);
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float v = c < C ? __ldg(x + (((long long)n * C + c) * H + h) * W + w) : 0.f;
+      split_h(v, hi[c], lo[c]);
+    }
+    const long long o = (((long long)n * out_H + h + top) * out_W + w + left) * 8;
+    *reinterpret_cast<uint4*>(ys + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(ys + ys_plane + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 // sparse rows: y = act(y + res) for the first *count rows, plus their split planes
 __global__ void f16s_sparse_finish_kernel(float* __restrict__ y, int y_ld, const float* __restrict__ res, int res_ld, int C,
                                           const int* __restrict__ count, int cap, int act, __half* __restrict__ ys, long long ys_plane) {
@@ -756,6 +777,20 @@ int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plan
   split_rows_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, x_ld, static_cast<__half*>(y_split), y_plane, y_ld, rows, cols / 4, row_count);
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_split_f16");
+  return TT_OK;
+}
+
+int tt_image_to_split8(const float* x, void* y_split, long long y_plane, int N, int C, int H, int W, int out_H, int out_W, int top,
+                       int left, tt_stream_t stream) {
+  TT_REQUIRE(x && y_split && C >= 1 && C <= 8 && top >= 0 && left >= 0 && top + H <= out_H && left + W <= out_W && y_plane % 8 == 0 &&
+                 (reinterpret_cast<uintptr_t>(y_split) & 15) == 0,
+             "tt_image_to_split8", "bad arguments");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return TT_OK;
+  const int nb = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+  image_to_split8_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, static_cast<__half*>(y_split), y_plane, C, H, W, out_H, out_W, top, left, total);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_image_to_split8");
   return TT_OK;
 }
 

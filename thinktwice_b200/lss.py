@@ -192,9 +192,9 @@ class LSS(nn.Module):
         e.broadcast_rows(g, cat.slice(4 * self.mid, self.mid))
         y = e.conv(cat, w['aspp_out'], name='dn.aspp.out', act=ACT_RELU)
         off = e.conv(y, w['dcn_off'], name='dn.dcn.off', pad=1)
-        col = e.fmap('dn.dcn.col', BN, H, W, 9 * self.mid)
+        col = e.out_map('dn.dcn.col', BN, H, W, 9 * self.mid, fmt='s')     # only the grouped GEMMs read the sampled columns
         lib.call('tt_dcn_im2col', _p(y.t), _p(off.t), off.ld, _p(col.t), BN, H, W, self.mid, 4)
-        e.sync_split(col)
+        e.finish_out(col)
         yd = e.fmap('dn.dcn.out', BN, H, W, self.mid)
         cg = 9 * self.mid // len(w['dcn'])
         for g, wg in enumerate(w['dcn']):                               # grouped conv = one dense GEMM per group slice
@@ -243,17 +243,18 @@ class LSS(nn.Module):
         # floats = one 32-float K slab of a 7x1 conv over 32 "channels" (x_ld = 4 < Cin = 32, row pitch x_hstride)
         im = imgs.reshape(B * N, *imgs.shape[2:])
         H0, W0 = im.shape[2:]
-        pb = e.nchw_to_nhwc_padded(im, 'img.nhwc', 4, 3, 3, 3, 5)
         Wp = W0 + 8
         if e.split:
             # scaled-split engine: 8 halves per pixel (3 channels + 5 zeros; TMA strides are multiples of 16 bytes), so a tap row
-            # of 7 px is 56 halves inside ONE 64-half K slab; the companion is zeroed once, only channels 0..3 are ever written
+            # of 7 px is 56 halves inside ONE 64-half K slab; the planes are written straight from the NCHW image, the zero border
+            # (zeroed once at allocation) is never touched
             rows = B * N * (H0 + 6) * Wp
             pbs = e.buf('img.nhwc#s8', (2, rows * 8), torch.float16, zero=True)
-            lib.call('tt_split_f16', _p(pb), C.c_longlong(4), _p(pbs), C.c_longlong(rows * 8), C.c_longlong(8), C.c_longlong(rows), 4, None)
+            lib.call('tt_image_to_split8', _p(im.contiguous()), _p(pbs), C.c_longlong(rows * 8), B * N, im.shape[1], H0, W0, H0 + 6, Wp, 3, 3)
             x = e.conv(FMap(None, B * N, H0 + 6, W0, 64, ld=8, s=pbs), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
                        x_hstride=Wp * 8, x_nstride=(H0 + 6) * Wp * 8, fmt='f')    # only the max-pool (an fp32 kernel) reads it
         else:
+            pb = e.nchw_to_nhwc_padded(im, 'img.nhwc', 4, 3, 3, 3, 5)
             x = e.conv(FMap(pb, B * N, H0 + 6, W0, 32, ld=4), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
                        x_hstride=Wp * 4, x_nstride=(H0 + 6) * Wp * 4)
         fpn = self._pafpn(self._backbone(x))

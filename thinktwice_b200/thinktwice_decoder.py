@@ -60,6 +60,7 @@ class ThinkTwiceDecoder(nn.Module):
         self.config, self.bev_h, self.bev_w, self.prefix = config, bev_h, bev_w, prefix
         self.T = config['pred_len']
         self.K = config['refine_num']
+        self.value_all_budget = 8 << 30     # bytes the merged value_proj output may take (else per-layer projection)
 
     # ------------------------------------------------------------------ weights
     def prepare(self, pk, eng, parent):
@@ -97,6 +98,7 @@ class ThinkTwiceDecoder(nn.Module):
             Wv, bv = pk.sd[c + 'deformable_attention.value_proj.weight'].double(), pk.sd[c + 'deformable_attention.value_proj.bias'].double()
             L['_value_w'] = Wv
             L['_value_b'] = [torch.stack([bv + Wv @ (cams[cam] + lvls[l]) for cam in range(4)]) for l in range(4)]    # [level] -> (4 cams, 256)
+            L['value'] = [pk.linear(c + 'deformable_attention.value_proj', bias=L['_value_b'][l].float().reshape(-1)) for l in range(4)]
             L['ffn_ln'] = (pk.vec(c + 'ffn.norm.weight'), pk.vec(c + 'ffn.norm.bias'))
             L['ffn1'], L['ffn2'] = pk.linear(c + 'ffn.w_1'), pk.linear(c + 'ffn.w_2')
             L['op_ln'] = (pk.vec(c + 'output_proj.0.weight'), pk.vec(c + 'output_proj.0.bias'))
@@ -158,6 +160,8 @@ class ThinkTwiceDecoder(nn.Module):
         (msda:474 per layer in the reference: the FPN maps are read once instead of K times, 4 launches instead of 4K)."""
         e = self.eng
         B, cams, nk, KC = meta['B'], 4, meta['num_keys'], self.K * 256
+        if B * cams * nk * KC * 4 > self.value_all_budget:           # e.g. B = 32: 21.8 GB for K = 5
+            return None
         value = e.buf('look.value_all', (B * cams, nk, KC))
         for l, m in enumerate(mlvl):
             out = FMap(value, B * cams, m.H, m.W, KC, KC, meta['lvl_start'][l] * KC)
@@ -183,14 +187,20 @@ class ThinkTwiceDecoder(nn.Module):
         q = e.layernorm(rows, *L['q_ln'], name='look.q_ln', out_ld=1544)
         q = e.linear(q.view(q.N, 1, 1, 1544), L['q1'], name='look.q1', act=ACT_GELU)
         q = e.linear(q, L['q3'], name='look.q', act=ACT_GELU)
-        # value_proj (msda:474): computed for all layers at once before the cascade (_values); layer k reads its channel block
+        # value_proj (msda:474): computed for all layers at once before the cascade (_values; layer k reads its channel block) when the
+        # K-fold value tensor fits the memory budget, else layer by layer into one reused buffer
         nk = meta['num_keys']
         value = meta['value_all']
+        if value is None:
+            value = e.buf('look.value', (B * cams, nk, 256))
+            for l, m in enumerate(mlvl):                             # one launch per level over all B*cams images
+                out = FMap(value, B * cams, m.H, m.W, 256, 256, meta['lvl_start'][l] * 256)
+                e.conv(m, L['value'][l], out=out, name=f'look.value{l}', y_nstride=nk * 256, bias_n_mod=cams)
         off = e.linear(q, L['off'], name='look.off')
         aw = e.linear(q, L['aw'], name='look.aw')
         att = e.fmap('look.att', B * cams * cap, 1, 1, 256)
         md = meta['msda_desc']
-        md.value_ld, md.value_coff = self.K * 256, k * 256
+        md.value_ld, md.value_coff = (self.K * 256, k * 256) if meta['value_all'] is not None else (0, 0)
         lib.call('tt_msda_forward', C.byref(md), _p(value), _p(off.t), _p(aw.t), _p(ref_re), _p(max_len), _p(att.t))
         # PositionwiseFeedForward (msda:197-214)
         h = e.layernorm(att, *L['ffn_ln'], name='look.ffn_ln')
