@@ -154,6 +154,8 @@ int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plan
  * is never written: zero the buffer once). */
 int tt_image_to_split8(const float* x, void* y_split, long long y_plane, int N, int C, int H, int W, int out_H, int out_W, int top,
                        int left, tt_stream_t stream);
+/* tt_upsample2x_bilinear_ac (lss.py:267) with the result written as split planes [2][N][2H][2W][C] only */
+int tt_upsample2x_bilinear_ac_split(const float* x, void* y_split, long long y_plane, int N, int H, int W, int C, tt_stream_t stream);
 /* split planes -> fp32 rows (hi + lo' / 2048): for a non-convolution kernel that must read a tensor stored as planes only */
 int tt_merge_f16(const void* x_split, long long x_plane, long long x_ld, float* y, long long y_ld, long long rows, int cols,
                  tt_stream_t stream);

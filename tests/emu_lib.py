@@ -209,6 +209,16 @@ class Emu:
             dst[:, top:top + H, left:left + W, Cc:] = 0
         return 0
 
+    def tt_upsample2x_bilinear_ac_split(self, x, y_split, y_plane, N, H, W, Cc, stream):
+        self.launches += 1
+        y_plane = _v(y_plane)
+        xin = x.flat()[:N * H * W * Cc].view(N, H, W, Cc).permute(0, 3, 1, 2)
+        up = F.interpolate(xin, scale_factor=2, mode='bilinear', align_corners=True).permute(0, 2, 3, 1).contiguous()
+        hi, lo = _split_f16(up)
+        y_split.flat()[:up.numel()].copy_(hi.reshape(-1))
+        Ptr(y_split.t, y_split.off + y_plane).flat()[:up.numel()].copy_(lo.reshape(-1))
+        return 0
+
     def tt_merge_f16(self, x_split, x_plane, x_ld, y, y_ld, rows, cols, stream):
         self.launches += 1
         x_plane, x_ld, y_ld, rows = _v(x_plane), _v(x_ld), _v(y_ld), _v(rows)

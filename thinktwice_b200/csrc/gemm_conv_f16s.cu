@@ -674,6 +674,41 @@ __global__ void image_to_split8_kernel(const float* __restrict__ x, __half* __re
   }
 }
 
+// nn.Upsample(scale_factor=2, bilinear, align_corners=True) (lss.py:267) from fp32 straight into split planes: the same arithmetic
+// as upsample2x_ac_kernel (elementwise.cu), no fp32 copy of the 4x larger map
+__global__ void upsample2x_split_kernel(const float4* __restrict__ x, __half* __restrict__ ys, long long ys_plane, int N, int H, int W, int C4) {
+  const int OH = 2 * H, OW = 2 * W;
+  const float sh = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+  const float sw = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  const long long total = (long long)N * OH * OW * C4;
+  bool sat = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C4;
+    long long t = i / C4;
+    const int ow = t % OW; t /= OW;
+    const int oh = t % OH;
+    const int n = t / OH;
+    const float fy = sh * oh, fx = sw * ow;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float4 a = __ldg(&x[((long long)(n * H + y0) * W + x0) * C4 + c]);
+    const float4 b = __ldg(&x[((long long)(n * H + y0) * W + x1) * C4 + c]);
+    const float4 cc = __ldg(&x[((long long)(n * H + y1) * W + x0) * C4 + c]);
+    const float4 dd = __ldg(&x[((long long)(n * H + y1) * W + x1) * C4 + c]);
+    float4 r;
+    r.x = hy * (hx * a.x + lx * b.x) + ly * (hx * cc.x + lx * dd.x);
+    r.y = hy * (hx * a.y + lx * b.y) + ly * (hx * cc.y + lx * dd.y);
+    r.z = hy * (hx * a.z + lx * b.z) + ly * (hx * cc.z + lx * dd.z);
+    r.w = hy * (hx * a.w + lx * b.w) + ly * (hx * cc.w + lx * dd.w);
+    uint2 hi, lo;
+    split4(r, hi, lo, sat);
+    *reinterpret_cast<uint2*>(ys + i * 4) = hi;
+    *reinterpret_cast<uint2*>(ys + ys_plane + i * 4) = lo;
+  }
+  if (sat) atomicAdd(&g_f16s_saturated, 1u);
+}
+
 // sparse rows: y = act(y + res) for the first *count rows, plus their split planes
 __global__ void f16s_sparse_finish_kernel(float* __restrict__ y, int y_ld, const float* __restrict__ res, int res_ld, int C,
                                           const int* __restrict__ count, int cap, int act, __half* __restrict__ ys, long long ys_plane) {
@@ -791,6 +826,18 @@ int tt_image_to_split8(const float* x, void* y_split, long long y_plane, int N, 
   image_to_split8_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, static_cast<__half*>(y_split), y_plane, C, H, W, out_H, out_W, top, left, total);
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_image_to_split8");
+  return TT_OK;
+}
+
+int tt_upsample2x_bilinear_ac_split(const float* x, void* y_split, long long y_plane, int N, int H, int W, int C, tt_stream_t stream) {
+  TT_REQUIRE(x && y_split && C % 4 == 0 && y_plane % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_split) & 7) == 0,
+             "tt_upsample2x_bilinear_ac_split", "C must be a multiple of 4, aligned pointers");
+  const long long total = (long long)N * 4 * H * W * (C / 4);
+  if (total == 0) return TT_OK;
+  const int nb = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+  upsample2x_split_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), static_cast<__half*>(y_split), y_plane, N, H, W, C / 4);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_upsample2x_bilinear_ac_split");
   return TT_OK;
 }
 

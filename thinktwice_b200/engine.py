@@ -383,18 +383,21 @@ class Engine:
             out = out.as_rows()
         return self.conv(xr, pw, out=out, name=name, act=act, res=res.as_rows() if res is not None else None)
 
-    def sparse_feats(self, name, rows, Cc):
-        """(fp32 rows [rows][C], split companion [2][rows*C] or None) for a sparse feature matrix."""
-        t = self.buf(name, (rows, Cc))
+    def sparse_feats(self, name, rows, Cc, f32=True):
+        """(fp32 rows [rows][C] or None, split companion [2][rows*C] or None) for a sparse feature matrix.  f32=False: rows that only
+        the output-stationary f16s convolutions read (operands and residuals from the planes) keep no fp32 copy."""
         sc = self.buf(name + '#s', (2, rows * Cc), torch.float16, zero=True) if self.split and Cc % 8 == 0 and Cc >= 32 else None
+        t = self.buf(name, (rows, Cc)) if (f32 or sc is None) else None
         return t, sc
 
-    def sparse_conv(self, feats, pw, rule, out, act=0, res=None, name=None, feats_s=None, out_s=None):
-        """tap-major sparse conv over a rulebook `rule` (dict from LidarNet._rulebook): feats [cap_in][Cin] -> out [cap_out][Cout].
-        feats_s / out_s: scaled-split companions of the input / output rows (f16s engine)."""
+    def sparse_conv(self, feats, pw, rule, out, act=0, res=None, name=None, feats_s=None, out_s=None, res_s=None):
+        """sparse conv over a rulebook `rule` (dict from LidarNet._rulebook): feats [cap_in][Cin] -> out [cap_out][Cout].
+        feats_s / out_s / res_s: scaled-split companions of the input / output / residual rows (f16s engine); with the output-
+        stationary form any of the fp32 tensors may be None (planes only)."""
         d = lib.SparseConvDesc()
         d.Cin, d.Cout, d.kvol = pw.Cin, pw.Cout, rule['kvol']
-        d.in_ld, d.out_ld, d.res_ld = feats.shape[1], out.shape[1], (res.shape[1] if res is not None else 0)
+        d.in_ld, d.out_ld = pw.Cin, pw.Cout                         # sparse feature matrices are dense rows
+        d.res_ld = pw.Cout if (res is not None or res_s is not None) else 0
         d.cap_out, d.pair_cap, d.act = rule['cap'], rule['cap'], act
         wide = pw.Cin >= 32 and pw.Cout >= 32 and rule['kvol'] <= 32
         use_h = (self.impl == lib.IMPL_F16S and pw.w_h is not None and feats_s is not None and wide and pw.Cin % 8 == 0 and d.in_ld % 8 == 0
@@ -411,11 +414,16 @@ class Engine:
             io.w_split, io.bias = _p(pw.w_h), _p(pw.bias)
             if res is not None:
                 io.res = _p(res)
-            io.y = _p(out)
+            elif res_s is not None:
+                io.res_split, io.res_plane = _p(res_s), res_s.numel() // 2
+            if out is not None:
+                io.y = _p(out)
             if out_s is not None:
                 io.y_split, io.y_plane = _p(out_s), out_s.numel() // 2
             lib.check(lib.load().tt_sparse_conv_os_f16s(C.byref(d), lib.ref(io), _p(rule['nbr']), _p(rule['count']), _stream()),
                       f'tt_sparse_conv_os_f16s[{name}]')
+        elif feats is None or out is None or (res is None and res_s is not None):
+            raise lib.TTError(f'sparse conv {name}: planes-only rows need the output-stationary f16s form')
         elif use_h:
             lib.check(lib.load().tt_sparse_conv_f16s(C.byref(d), _p(feats_s), C.c_longlong(feats_s.numel() // 2), _p(pw.w_h), _p(pw.bias), _p(res),
                                                      _p(rule['pairs_in']), _p(rule['pairs_out']), _p(rule['pair_count']), _p(rule['count']), _p(out),
@@ -464,6 +472,11 @@ class Engine:
     def upsample2x(self, x, name, fmt=None):
         assert x.ld == x.C and x.coff == 0
         self.need_f32(x, 'upsample2x')
+        if fmt == 's' and self.split:
+            out = self.fmap(name, x.N, 2 * x.H, 2 * x.W, x.C, fmt='s')
+            if out.t is None:                                        # planes only: written directly, no fp32 copy of the 4x larger map
+                lib.call('tt_upsample2x_bilinear_ac_split', _p(x.t), _p(out.s), C.c_longlong(out.s.numel() // 2), x.N, x.H, x.W, x.C)
+                return out
         out = self.out_map(name, x.N, 2 * x.H, 2 * x.W, x.C, fmt)
         lib.call('tt_upsample2x_bilinear_ac', _p(_t(x)), _p(_t(out)), x.N, x.H, x.W, x.C)
         return self.finish_out(out)

@@ -148,19 +148,20 @@ class LidarNet(nn.Module):
             for j, layer in enumerate(st):
                 if layer[0] == 'block':
                     _, w1, w2 = layer
-                    t, ts = e.sparse_feats(f'sp.l{i}.t', rb['cap'], w1.Cout)
+                    po = rb.get('nbr') is not None                   # planes-only rows: the output-stationary convs need no fp32 copy
+                    t, ts = e.sparse_feats(f'sp.l{i}.t', rb['cap'], w1.Cout, f32=not po)
                     e.sparse_conv(x, w1, rb, t, act=ACT_RELU, name=f'{i}.{j}.conv1', feats_s=xs, out_s=ts)
-                    o, os_ = e.sparse_feats(f'sp.l{i}.o{j % 2}', rb['cap'], w2.Cout)
-                    e.sparse_conv(t, w2, rb, o, act=ACT_RELU, res=x, name=f'{i}.{j}.conv2', feats_s=ts, out_s=os_)
+                    o, os_ = e.sparse_feats(f'sp.l{i}.o{j % 2}', rb['cap'], w2.Cout, f32=not po)
+                    e.sparse_conv(t, w2, rb, o, act=ACT_RELU, res=x, res_s=xs if x is None else None, name=f'{i}.{j}.conv2', feats_s=ts, out_s=os_)
                     x, xs = o, os_
                 else:
                     _, wc, k, s, p = layer
                     rd = self._rulebook(f'd{i}', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], k, s, p, False, form(wc.Cin))
-                    o, os_ = e.sparse_feats(f'sp.l{i + 1}.x', rd['cap'], wc.Cout)
-                    e.sparse_conv(x, wc, rd, o, act=ACT_RELU, name=f'{i}.{j}.down', feats_s=xs, out_s=os_)
-                    x, xs = o, os_
                     # rulebook of the SubM convs at the new resolution
-                    rb = self._rulebook(f'l{i + 1}', B, rd['coords'], rd['count'], rd['cap'], rd['shape'], (3, 3, 3), (1, 1, 1), (1, 1, 1), True, form(wc.Cout))
+                    rb2 = self._rulebook(f'l{i + 1}', B, rd['coords'], rd['count'], rd['cap'], rd['shape'], (3, 3, 3), (1, 1, 1), (1, 1, 1), True, form(wc.Cout))
+                    o, os_ = e.sparse_feats(f'sp.l{i + 1}.x', rd['cap'], wc.Cout, f32=rd.get('nbr') is None or rb2.get('nbr') is None)
+                    e.sparse_conv(x, wc, rd, o, act=ACT_RELU, name=f'{i}.{j}.down', feats_s=xs, out_s=os_)
+                    x, xs, rb = o, os_, rb2
         ro = self._rulebook('out', B, rb['coords'], rb['count'], rb['cap'], rb['shape'], self.k_out, (2, 1, 1), (0, 0, 0), False, form(self.w_out.Cin))
         o, _ = e.sparse_feats('sp.out.x', ro['cap'], self.w_out.Cout)
         x = e.sparse_conv(x, self.w_out, ro, o, act=ACT_RELU, name='conv_out', feats_s=xs)

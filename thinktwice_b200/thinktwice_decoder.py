@@ -74,6 +74,11 @@ class ThinkTwiceDecoder(nn.Module):
                         ('value_branch_ctrl', 3), ('policy_head', 2), ('dist_mu', 2), ('dist_sigma', 2)):
             w[name] = mlp(name, n)
         w['fpn_linear'] = [pk.conv(f'{p}fpn_linear{i}') for i in range(4)]
+        # fpn_linear is followed by value_proj with nothing in between (thinktwice_decoder.py:442-450 -> msda:474): the value tensor is
+        # computed from the FPN maps directly with the composed map (Wv Wf) x + Wv bf + ..., so the projected maps `mlvl` are only read by
+        # the fp32 bilinear gather of the look points
+        Wf = [pk.sd[f'{p}fpn_linear{i}.weight'].double().reshape(256, -1) for i in range(4)]
+        bf = [pk.sd[f'{p}fpn_linear{i}.bias'].double() for i in range(4)]
         self.temb, self.semb = pk.vec(p + 'temporal_embedding'), pk.vec(p + 'static_embedding')
         cams, lvls = pk.sd[p + 'cams_embeds'].double(), pk.sd[p + 'level_embeds'].double()
         # GRU input planes are laid out [state 32 | x 6 | pad 2] (vector-aligned); permute the conv weights to match
@@ -96,9 +101,10 @@ class ThinkTwiceDecoder(nn.Module):
             # The K layers' value projections depend only on the FPN maps, not on the cascade: they are packed as ONE
             # 256 -> K*256 projection per level (self.value_all, built after this loop) and run once, ahead of the cascade.
             Wv, bv = pk.sd[c + 'deformable_attention.value_proj.weight'].double(), pk.sd[c + 'deformable_attention.value_proj.bias'].double()
-            L['_value_w'] = Wv
-            L['_value_b'] = [torch.stack([bv + Wv @ (cams[cam] + lvls[l]) for cam in range(4)]) for l in range(4)]    # [level] -> (4 cams, 256)
-            L['value'] = [pk.linear(c + 'deformable_attention.value_proj', bias=L['_value_b'][l].float().reshape(-1)) for l in range(4)]
+            L['_value_w'] = [Wv @ Wf[l] for l in range(4)]          # [level] -> (256, C_fpn_l)
+            L['_value_b'] = [torch.stack([bv + Wv @ (bf[l] + cams[cam] + lvls[l]) for cam in range(4)]) for l in range(4)]    # [level] -> (4 cams, 256)
+            L['value'] = [pk.linear(c + 'deformable_attention.value_proj', weight=L['_value_w'][l], bias=L['_value_b'][l].float().reshape(-1))
+                          for l in range(4)]
             L['ffn_ln'] = (pk.vec(c + 'ffn.norm.weight'), pk.vec(c + 'ffn.norm.bias'))
             L['ffn1'], L['ffn2'] = pk.linear(c + 'ffn.w_1'), pk.linear(c + 'ffn.w_2')
             L['op_ln'] = (pk.vec(c + 'output_proj.0.weight'), pk.vec(c + 'output_proj.0.bias'))
@@ -110,8 +116,8 @@ class ThinkTwiceDecoder(nn.Module):
             L['bev_up'] = (pk.conv(q + 'BEV_feat_update_module.0'), pk.conv(q + 'BEV_feat_update_module.2'))
             L['flat_up'] = (pk.linear(q + 'flattened_BEV_feat_update_module.0'), pk.linear(q + 'flattened_BEV_feat_update_module.2'))
             self.layers.append(L)
-        Wcat = torch.cat([L['_value_w'] for L in self.layers], 0)              # (K*256, 256): layer k owns output channels [256k, 256k+256)
-        self.value_all = [pk.linear(p + 'value_proj_all', weight=Wcat,
+        # (K*256, C_fpn_l) per level: layer k owns output channels [256k, 256k+256)
+        self.value_all = [pk.linear(p + 'value_proj_all', weight=torch.cat([L['_value_w'][l] for L in self.layers], 0),
                                     bias=torch.cat([L['_value_b'][l] for L in self.layers], 1).float().reshape(-1))
                           for l in range(4)]                            # per level: bias table [4 cams][K*256] (bias_n_mod = 4)
         for L in self.layers:
@@ -165,7 +171,7 @@ class ThinkTwiceDecoder(nn.Module):
         value = e.buf('look.value_all', (B * cams, nk, KC))
         for l, m in enumerate(mlvl):
             out = FMap(value, B * cams, m.H, m.W, KC, KC, meta['lvl_start'][l] * KC)
-            e.conv(m, self.value_all[l], out=out, name=f'look.value{l}', y_nstride=nk * KC, bias_n_mod=cams)
+            e.conv(meta['fpn'][l], self.value_all[l], out=out, name=f'look.value{l}', y_nstride=nk * KC, bias_n_mod=cams)
         return value
 
     def _look(self, L, k, wp, ctrl_sp, meas, flat, mlvl, meta):
@@ -195,7 +201,7 @@ class ThinkTwiceDecoder(nn.Module):
             value = e.buf('look.value', (B * cams, nk, 256))
             for l, m in enumerate(mlvl):                             # one launch per level over all B*cams images
                 out = FMap(value, B * cams, m.H, m.W, 256, 256, meta['lvl_start'][l] * 256)
-                e.conv(m, L['value'][l], out=out, name=f'look.value{l}', y_nstride=nk * 256, bias_n_mod=cams)
+                e.conv(meta['fpn'][l], L['value'][l], out=out, name=f'look.value{l}', y_nstride=nk * 256, bias_n_mod=cams)
         off = e.linear(q, L['off'], name='look.off')
         aw = e.linear(q, L['aw'], name='look.aw')
         att = e.fmap('look.att', B * cams * cap, 1, 1, 256)
@@ -241,8 +247,9 @@ class ThinkTwiceDecoder(nn.Module):
         e.copy_cols(FMap(wp.t, B, 1, 1, T * 2), wp_all.slice(0, T * 2)); e.copy_cols(FMap(ctrl.t, B, 1, 1, T * 4), ctrl_all.slice(0, T * 4))
 
         # ---- Look-module inputs (thinktwice_decoder.py:442-450)
-        mlvl = [e.conv(fpn[i], w['fpn_linear'][i], name=f'dec.mlvl{i}') for i in range(4)]
+        mlvl = [e.conv(fpn[i], w['fpn_linear'][i], name=f'dec.mlvl{i}', fmt='f') for i in range(4)]
         meta = self._look_meta(B, mlvl)
+        meta['fpn'] = fpn
         meta['value_all'] = self._values(mlvl, meta)
 
         cur_bev, cur_flat = bev, flat
