@@ -146,6 +146,11 @@ typedef struct {
   float* y; void* y_split; long long y_plane; /* outputs */
 } tt_f16s_io;
 int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stream);
+/* Thin 1x1 stride-1 convolution (Cin <= 64, Cout <= 64, no residual, contiguous pixels) as a per-pixel fp32 mat-vec: one thread per
+ * pixel reads its channel row from the split planes `io->x_split`, multiplies with the fp32 K-major weights `w_kmajor` [Cin][Cout] (the
+ * tt_conv2d impl 0/1 layout) and writes fp32 rows and / or planes.  For maps so large and channels so few that 128 x 64 tensor-core tiles
+ * are all overhead (the segmentation head at 224 x 448). */
+int tt_pointwise_f16s(const tt_conv_desc* d, const tt_f16s_io* io, const float* w_kmajor, tt_stream_t stream);
 /* fp32 rows [rows][x_ld] (first `cols` columns) -> split planes [2][rows][y_ld]; only the first *row_count rows when given */
 int tt_split_f16(const float* x, long long x_ld, void* y_split, long long y_plane, long long y_ld, long long rows, int cols,
                  const int* row_count, tt_stream_t stream);

@@ -110,7 +110,7 @@ class Emu:
         raise NotImplementedError(f'emu_lib: {name}')
 
     # ------------------------------------------------------------------ conv / linear
-    def tt_conv2d(self, d, x, w, bias, res, res2, gather, m_count, y, ws, stream, f16s=None):
+    def tt_conv2d(self, d, x, w, bias, res, res2, gather, m_count, y, ws, stream, f16s=None, kmajor_w=False):
         d = _desc(d)
         self.launches += 1
         assert not gather and not m_count
@@ -125,7 +125,7 @@ class Emu:
             lo = _pix_view(Ptr(x.t, x.off + f16s.x_plane), d.N, d.H, Wv, d.x_ld, d.x_nstride, d.x_hstride, C_).double()
             return hi + lo / 2048.0
         xin = xview(d.Cin).permute(0, 3, 1, 2) if d.x_ld >= d.Cin else None
-        if f16s is not None:                                           # [2][Cout][taps][Cin8] scaled-split half planes
+        if f16s is not None and not kmajor_w:                          # [2][Cout][taps][Cin8] scaled-split half planes
             c8 = -(-d.Cin // 8) * 8
             planes = w.flat()[:2 * d.Cout * taps * c8].view(2, d.Cout, taps, c8).double()
             wt = (planes[0] + planes[1] / 2048.0)[..., :d.Cin].reshape(d.Cout, d.KH, d.KW, d.Cin).permute(0, 3, 1, 2)
@@ -187,6 +187,18 @@ class Emu:
         assert io.x_split.t.dtype == torch.float16 and io.w_split.t.dtype == torch.float16
         assert io.y or io.y_split
         return self.tt_conv2d(d, io.x_split, io.w_split, io.bias, io.res, io.res2, NULL, NULL, io.y, NULL, stream, f16s=io)
+
+    def tt_pointwise_f16s(self, d, io, w_kmajor, stream):
+        """thin 1x1 conv: split-plane input, fp32 K-major weights [Cin][Cout]."""
+        dd = _desc(d)
+        assert dd.KH == 1 and dd.KW == 1 and dd.Cin <= 64 and dd.Cout <= 64 and not io.res and not io.res_split
+        old = dd.impl
+        dd.impl = 1                                                    # weights in the SIMT layout
+        io2 = IO()
+        io2.__dict__.update(io.__dict__)
+        rc = self.tt_conv2d(d, io.x_split, w_kmajor, io.bias, NULL, NULL, NULL, NULL, io.y, NULL, stream, f16s=io2, kmajor_w=True)
+        dd.impl = old
+        return rc
 
     def tt_split_f16(self, x, x_ld, y_split, y_plane, y_ld, rows, cols, row_count, stream):
         self.launches += 1

@@ -306,3 +306,31 @@ def test_f16s_split_only_tensors_chain_through_convs_residuals_and_copies():
     assert up.t is None
     ref_up = F.interpolate(torch.cat([r2, r1], 1), scale_factor=2, mode='bilinear', align_corners=True)
     assert relerr(up.nchw(), ref_up) < TOL
+
+
+@pytest.mark.parametrize('Cin,Cout,act', [(12, 64, 1), (64, 32, 0), (64, 12, 0), (32, 32, 1), (64, 64, 1)])
+def test_f16s_thin_pointwise_conv_matches_fp64(Cin, Cout, act):
+    """tt_pointwise_f16s: thin 1x1 heads over large maps as a per-pixel fp32 mat-vec (one thread per pixel, planes in, fp32 + planes out)."""
+    from thinktwice_b200 import lib
+    from thinktwice_b200.weights import Packer
+    gen = torch.Generator().manual_seed(Cin * 100 + Cout)
+    N, H, W = 2, 96, 160
+    x = torch.randn(N, Cin, H, W, generator=gen)
+    w = torch.randn(Cout, Cin, 1, 1, generator=gen) * Cin ** -0.5
+    b = torch.randn(Cout, generator=gen)
+    eng = engine()
+    eng.thin_min_rows = 1
+    cp = 32 if Cout < 32 else None                                       # the model pads thin heads to 32 output channels
+    pw = Packer({'c.weight': w, 'c.bias': b}, torch.device('cuda:0'), tc_mode=IMPL).conv('c', cout_pad=cp)
+    xf = to_fmap_s(eng, 'pw.x', x.cuda(), ld=max(32, -(-Cin // 8) * 8))
+    n0 = lib.launch_count()
+    y = eng.conv(xf, pw, name='pw.y', act=act)
+    torch.cuda.synchronize()
+    assert lib.launch_count() - n0 == (2 if pw.Cout > 32 else 1)
+    ref = F.conv2d(x.double(), w.double(), b.double())
+    ref = F.relu(ref) if act else ref
+    got = y.nchw()[:, :Cout]
+    assert relerr(got, ref) < 2e-6
+    assert relerr(split_value(y)[:, :Cout], got) < 6e-7
+    if pw.Cout > Cout:
+        assert float(y.nchw()[:, Cout:].abs().max()) == 0

@@ -518,25 +518,35 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         o1[i] = row_r1[rr];
         o2[i] = row_r2[rr];
       }
+      // residual / bias values travel one slab AHEAD of their use (software pipeline of depth 2): the loads of slab sl + 1 are in
+      // flight while slab sl is transposed, finished and stored
+      float4 ra[4], rb[4], ra_n[4], rb_n[4], bv0, bv0_n;
+      auto load_side = [&](int sl, float4* a, float4* b, float4& bv) {
+        const int col = n0 + sl * SLAB + cl;
+        const bool live = col < d.Cout && !(p.dbg & 1);
+        bv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          b[i] = a[i];
+          if (live && (fl[i] & 1)) {
+            if (p.res) a[i] = *reinterpret_cast<const float4*>(p.res + o1[i] + col);
+            else if (p.res_s) a[i] = load_split4(p.res_s + o1[i] + col, p.res_plane);
+            if (p.res2) b[i] = *reinterpret_cast<const float4*>(p.res2 + o2[i] + col);
+            else if (p.res2_s) b[i] = load_split4(p.res2_s + o2[i] + col, p.res2_plane);
+          }
+        }
+        if (live && p.bias && !d.bias_n_mod) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));   // one bias vector: once per slab
+      };
+      load_side(0, ra_n, rb_n, bv0_n);
 #pragma unroll
       for (int sl = 0; sl < HN / SLAB; ++sl) {
         const int col = n0 + sl * SLAB + cl;
         const bool live = col < d.Cout && !(p.dbg & 1);
-        // residual / bias loads of this slab are issued BEFORE the shared-memory transposition so that the two latencies overlap
-        float4 ra[4], rb[4];
-        float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          rb[i] = ra[i];
-          if (live && (fl[i] & 1)) {
-            if (p.res) ra[i] = *reinterpret_cast<const float4*>(p.res + o1[i] + col);
-            else if (p.res_s) ra[i] = load_split4(p.res_s + o1[i] + col, p.res_plane);
-            if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + o2[i] + col);
-            else if (p.res2_s) rb[i] = load_split4(p.res2_s + o2[i] + col, p.res2_plane);
-          }
-        }
-        if (live && p.bias && !d.bias_n_mod) bv0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));   // one bias vector: once per slab
+        for (int i = 0; i < 4; ++i) { ra[i] = ra_n[i]; rb[i] = rb_n[i]; }
+        bv0 = bv0_n;
+        if (sl + 1 < HN / SLAB) load_side(sl + 1, ra_n, rb_n, bv0_n);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < SLAB; j += 4)
@@ -709,6 +719,72 @@ __global__ void upsample2x_split_kernel(const float4* __restrict__ x, __half* __
   if (sat) atomicAdd(&g_f16s_saturated, 1u);
 }
 
+// Thin 1x1 convolutions (Cin <= 64, Cout <= 64) over large maps: 128 x 64 tensor-core tiles spend their time in per-tile overheads
+// there (one K stage per tile; seg / seg->feature heads at 224 x 448: ~10 % of the HBM roof), while the arithmetic is a per-pixel
+// 64 x 64 mat-vec at most.  One thread = one pixel: it streams its channel row from the split planes (full 128-byte lines), keeps
+// the COUT accumulators in registers (fp32 FFMA against fp32 weights broadcast from shared memory: exact products, no operand
+// split needed) and stores its output row (fp32 and / or planes).
+template <int COUT>
+__global__ void __launch_bounds__(256) pointwise_f16s_kernel(const __half* __restrict__ xs, long long xs_plane, int x_ld, int Cin,
+                                                              const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                                              float* __restrict__ y, __half* __restrict__ ys, long long ys_plane, int y_ld,
+                                                              int act, long long npix, int co0) {
+  __shared__ __align__(16) float ws[64 * COUT];                      // [k][co0 + co], rows beyond Cin / columns beyond Cout are zero
+  __shared__ float bs[COUT];
+  const int K8 = (Cin + 7) / 8 * 8;
+  for (int i = threadIdx.x; i < 64 * COUT; i += blockDim.x) {
+    const int k = i / COUT, co = i - k * COUT;
+    ws[i] = (k < Cin && co0 + co < Cout) ? w[(long long)k * Cout + co0 + co] : 0.f;
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = (bias && co0 + i < Cout) ? bias[co0 + i] : 0.f;
+  __syncthreads();
+  bool sat = false;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = bs[co];
+    const __half* xr = xs + pix * x_ld;
+    for (int k0 = 0; k0 < K8; k0 += 8) {
+      const uint4 h = *reinterpret_cast<const uint4*>(xr + k0);
+      const uint4 l = *reinterpret_cast<const uint4*>(xr + xs_plane + k0);
+      const __half2* hp = reinterpret_cast<const __half2*>(&h);
+      const __half2* lp = reinterpret_cast<const __half2*>(&l);
+      float xv[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(hp[j]), b = __half22float2(lp[j]);
+        xv[2 * j] = fmaf(b.x, LO_INV, a.x);
+        xv[2 * j + 1] = fmaf(b.y, LO_INV, a.y);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(&ws[(k0 + j) * COUT]);
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 wv = wr[c4];                                    // same address in every lane: shared-memory broadcast
+          acc[4 * c4] = fmaf(xv[j], wv.x, acc[4 * c4]);
+          acc[4 * c4 + 1] = fmaf(xv[j], wv.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(xv[j], wv.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(xv[j], wv.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c4 = 0; c4 < COUT / 4; ++c4) {
+      if (co0 + 4 * c4 >= Cout) break;
+      const float4 o = make_float4(tt_act(acc[4 * c4], act), tt_act(acc[4 * c4 + 1], act), tt_act(acc[4 * c4 + 2], act), tt_act(acc[4 * c4 + 3], act));
+      if (y) *reinterpret_cast<float4*>(y + pix * y_ld + co0 + 4 * c4) = o;
+      if (ys) {
+        uint2 hi, lo;
+        split4(o, hi, lo, sat);
+        *reinterpret_cast<uint2*>(ys + pix * y_ld + co0 + 4 * c4) = hi;
+        *reinterpret_cast<uint2*>(ys + ys_plane + pix * y_ld + co0 + 4 * c4) = lo;
+      }
+    }
+  }
+  if (sat) atomicAdd(&g_f16s_saturated, 1u);
+}
+
 // sparse rows: y = act(y + res) for the first *count rows, plus their split planes
 __global__ void f16s_sparse_finish_kernel(float* __restrict__ y, int y_ld, const float* __restrict__ res, int res_ld, int C,
                                           const int* __restrict__ count, int cap, int act, __half* __restrict__ ys, long long ys_plane) {
@@ -838,6 +914,39 @@ int tt_upsample2x_bilinear_ac_split(const float* x, void* y_split, long long y_p
   upsample2x_split_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), static_cast<__half*>(y_split), y_plane, N, H, W, C / 4);
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_upsample2x_bilinear_ac_split");
+  return TT_OK;
+}
+
+int tt_pointwise_f16s(const tt_conv_desc* d, const tt_f16s_io* io, const float* w_kmajor, tt_stream_t stream) {
+  TT_REQUIRE(d && io && io->x_split && w_kmajor && (io->y || io->y_split), "tt_pointwise_f16s", "null argument");
+  const long long xhs = d->x_hstride ? d->x_hstride : (long long)d->W * d->x_ld;
+  const long long xns = d->x_nstride ? d->x_nstride : (long long)d->H * xhs;
+  const bool ok = d->KH == 1 && d->KW == 1 && d->stride == 1 && d->pad == 0 && d->groups == 1 && d->Cin <= 64 && d->Cout <= 64 && d->Cout % 4 == 0 &&
+                  d->x_ld % 8 == 0 && (d->Cin + 7) / 8 * 8 <= d->x_ld && d->y_ld % 4 == 0 && d->y_coff % 4 == 0 && io->x_plane % 8 == 0 && io->y_plane % 4 == 0 &&
+                  xhs == (long long)d->W * d->x_ld && xns == (long long)d->H * xhs && d->y_nstride == 0 && d->oy_mul == 1 && d->ox_mul == 1 &&
+                  d->oy_add == 0 && d->ox_add == 0 && d->yH == d->OH && d->yW == d->OW && d->OH == d->H && d->OW == d->W &&
+                  d->res_mode == TT_RES_NONE && !io->res && !io->res_split && !io->res2 && !io->res2_split && d->bias_n_mod == 0 &&
+                  ((reinterpret_cast<uintptr_t>(io->x_split) | reinterpret_cast<uintptr_t>(io->y)) & 15) == 0 && (reinterpret_cast<uintptr_t>(io->y_split) & 7) == 0;
+  if (!ok) {
+    tt_set_error("tt_pointwise_f16s: needs a dense 1x1 stride-1 conv with Cin, Cout <= 64 (Cout %% 4), no residual, contiguous pixels");
+    return TT_ERR_UNSUPPORTED;
+  }
+  const long long npix = (long long)d->N * d->H * d->W;
+  if (npix == 0) return TT_OK;
+  const int nb = (int)((npix + 255) / 256 > 148 * 8 ? 148 * 8 : (npix + 255) / 256);
+  const __half* xs = static_cast<const __half*>(io->x_split);
+  __half* ys = static_cast<__half*>(io->y_split);
+  float* y = io->y ? io->y + d->y_coff : nullptr;
+  if (ys) ys += d->y_coff;
+  cudaStream_t st = (cudaStream_t)stream;
+  // 32 output channels per pass (register budget: 2 CTAs per SM); wider layers take two passes over the (small) input rows
+  for (int co0 = 0; co0 < d->Cout; co0 += 32) {
+    if (d->Cout <= 16) pointwise_f16s_kernel<16><<<nb, 256, 0, st>>>(xs, io->x_plane, d->x_ld, d->Cin, w_kmajor, io->bias, d->Cout, y, ys, io->y_plane, d->y_ld, d->act, npix, co0);
+    else pointwise_f16s_kernel<32><<<nb, 256, 0, st>>>(xs, io->x_plane, d->x_ld, d->Cin, w_kmajor, io->bias, d->Cout, y, ys, io->y_plane, d->y_ld, d->act, npix, co0);
+    if (co0) ++g_tt_launches;
+  }
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_pointwise_f16s");
   return TT_OK;
 }
 

@@ -129,6 +129,7 @@ class Engine:
         self.overlap = True         # run independent branches (side_branch) concurrently
         self.marks = None           # bench.py: list of (segment name, event) recorded by mark() in a serial eager step
         self.tc_min_rows = 512
+        self.thin_min_rows = 1 << 16   # rows from which a thin (Cin, Cout <= 64) 1x1 conv runs as a per-pixel mat-vec
         self.tc_strides = (1, 2)
         self.split = impl == lib.IMPL_F16S   # feature maps carry a scaled-split fp16 companion (gemm_conv_f16s.cu)
         self.stats = {'late_split': 0}
@@ -337,6 +338,10 @@ class Engine:
         if self.prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
+        # thin 1x1 heads over large maps: per-pixel fp32 mat-vec instead of 128-row tensor-core tiles (tt_pointwise_f16s)
+        thin = (use_h and pw.KH == 1 and pw.KW == 1 and stride == 1 and pad == 0 and pw.Cin <= 64 and pw.Cout <= 64 and res is None and res2 is None
+                and scatter is None and not x_nstride and not x_hstride and not y_nstride and not bias_n_mod and xs.ld >= -(-pw.Cin // 8) * 8
+                and d.N * OH * OW >= self.thin_min_rows)
         if use_h:
             io = lib.F16sIO()
             io.x_split, io.x_plane = _ps(xs)[0], xs.s.numel() // 2
@@ -356,7 +361,10 @@ class Engine:
                 io.y = _p(self.scratch_f32(out.s.numel() // 2), out.coff)
             if out.s is not None:
                 io.y_split, io.y_plane = _p(out.s, out.coff), out.s.numel() // 2
-            lib.check(lib.load().tt_conv2d_f16s(C.byref(d), lib.ref(io), _stream()), f'tt_conv2d_f16s[{name}]')
+            if thin:
+                lib.check(lib.load().tt_pointwise_f16s(C.byref(d), lib.ref(io), _p(pw.w), _stream()), f'tt_pointwise_f16s[{name}]')
+            else:
+                lib.check(lib.load().tt_conv2d_f16s(C.byref(d), lib.ref(io), _stream()), f'tt_conv2d_f16s[{name}]')
         else:
             pres = _p(res.t, res.coff) if res is not None else None
             pres2 = _p(res2.t, res2.coff) if res2 is not None else None
