@@ -131,8 +131,8 @@ struct HArgs {
 // GM (gather mode): 0 = dense convolution (TMA box loads); 1 = tap-major sparse convolution (work item = one tap's pair tile,
 // red.add epilogue); 2 = output-stationary sparse convolution (work item = an output-row tile, K runs over ALL taps through the
 // neighbour table, plain fused epilogue — no atomics, no init / finish passes; pays for empty (row, tap) slots with zero rows).
-template <int BN, int STAGES, int GM, bool PAIR>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int BN, int STAGES, int GM, bool PAIR, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = BM * KE * 2;                    // 16 KB per plane
@@ -142,7 +142,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr int TMEM_COLS = 2 * ACC_COLS;                 // ping-pong
   constexpr int SLAB = 16;
   constexpr int PITCH = SLAB + 4;
-  constexpr int HN = BN / 2;
+  constexpr int HN = BN / (EW / 4);                        // columns owned by one epilogue warp (EW / 4 warps per TMEM lane quarter)
+  constexpr int RPP = EW == 16 ? 16 : 32;                 // rows per transposition phase: the slab buffers stay 20 KB in total
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* tile_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);              // [8 warps][32 rows][PITCH]
   long long* row_y = reinterpret_cast<long long*>(tile_all + 8 * 32 * PITCH);
@@ -173,7 +174,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (GM == 1 && threadIdx.x == 64) {
@@ -402,7 +403,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long long yns = d.y_nstride ? d.y_nstride : (long long)d.yH * d.yW * d.y_ld;
     const int HWo = d.OH * d.OW;
-    float* tile = tile_all + (warp - 2) * 32 * PITCH;
+    float* tile = tile_all + (warp - 2) * RPP * PITCH;
     bool sat = false;
     int cg = 0;
     for (int pt = pair0; pt < total_pairs; pt += pair_step) {
@@ -491,19 +492,30 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&acc_full[b], (cg >> 1) & 1);
         tcgen05_fence_after();
         const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * ACC_COLS + half * HN);
+        if constexpr (EW == 16) {                              // register budget of the 576-thread variant: 16 columns at a time
 #pragma unroll
-        for (int c0 = 0; c0 < HN; c0 += 32) {
-          uint32_t v[32], u[32];
-          tmem_ld32(t_main + c0, v);
-          tmem_ld32(t_main + BN + c0, u);
+          for (int c0 = 0; c0 < HN; c0 += 16) {
+            uint32_t v[16], u[16];
+            tmem_ld16(t_main + c0, v);
+            tmem_ld16(t_main + BN + c0, u);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c0 + j] += fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j]));   // fp32 RN
+            for (int j = 0; j < 16; ++j) sum[c0 + j] += fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j]));
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < HN; c0 += 32) {
+            uint32_t v[32], u[32];
+            tmem_ld32(t_main + c0, v);
+            tmem_ld32(t_main + BN + c0, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j]));   // fp32 RN
+          }
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       const int sub = lane >> 2, cl = (lane & 3) * 4;
       // the 4 rows this lane stores (row groups of 8) are the same for every column slab: their table entries are read ONCE
       // per tile into registers (the profile showed the per-slab table reloads and the residual round trips as the epilogue's
@@ -533,43 +545,51 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (live && (fl[i] & 1)) {
             if (p.res) ra[i] = *reinterpret_cast<const float4*>(p.res + o1[i] + col);
             else if (p.res_s) ra[i] = load_split4(p.res_s + o1[i] + col, p.res_plane);
-            if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + o2[i] + col);
-            else if (p.res2_s) rb[i] = load_split4(p.res2_s + o2[i] + col, p.res2_plane);
+            if constexpr (EW != 16) {                           // (the 16-warp variant is not launched for layers with a second residual)
+              if (p.res2) rb[i] = *reinterpret_cast<const float4*>(p.res2 + o2[i] + col);
+              else if (p.res2_s) rb[i] = load_split4(p.res2_s + o2[i] + col, p.res2_plane);
+            }
           }
         }
         if (live && p.bias && !d.bias_n_mod) bv0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));   // one bias vector: once per slab
-        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < SLAB; j += 4)
-          *reinterpret_cast<float4*>(&tile[lane * PITCH + j]) =
-              make_float4(sum[sl * SLAB + j], sum[sl * SLAB + j + 1], sum[sl * SLAB + j + 2], sum[sl * SLAB + j + 3]);
-        __syncwarp();
-        if (live) {
+        for (int ph = 0; ph < 32 / RPP; ++ph) {
+          __syncwarp();
+          if (lane / RPP == ph) {                                // (RPP == 32: every lane) this lane's row goes through the buffer now
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (!(fl[i] & 1)) continue;
-            const float4 acc4 = *reinterpret_cast<const float4*>(&tile[(i * 8 + sub) * PITCH + cl]);
-            float4 bv = bv0;
-            if (p.bias && d.bias_n_mod) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout + col));
-            float4 o = make_float4(acc4.x + bv.x + ra[i].x + rb[i].x, acc4.y + bv.y + ra[i].y + rb[i].y,
-                                   acc4.z + bv.z + ra[i].z + rb[i].z, acc4.w + bv.w + ra[i].w + rb[i].w);
-            const long long eo = yo[i] + col;
-            if (GM == 1 || p.splits > 1) {                     // taps / K splits race on an output row: red.add (fp32 only)
-              tt_red_add_v4(p.y + eo, o.x, o.y, o.z, o.w);
-            } else {
-              o = make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
-              if (p.y) *reinterpret_cast<float4*>(p.y + eo) = o;
-              if (p.ys) {
-                uint2 hi, lo;
-                split4(o, hi, lo, sat);
-                *reinterpret_cast<uint2*>(p.ys + eo) = hi;
-                *reinterpret_cast<uint2*>(p.ys + p.ys_plane + eo) = lo;
+            for (int j = 0; j < SLAB; j += 4)
+              *reinterpret_cast<float4*>(&tile[(lane % RPP) * PITCH + j]) =
+                  make_float4(sum[sl * SLAB + j], sum[sl * SLAB + j + 1], sum[sl * SLAB + j + 2], sum[sl * SLAB + j + 3]);
+          }
+          __syncwarp();
+          if (live) {
+#pragma unroll
+            for (int ii = 0; ii < RPP / 8; ++ii) {
+              const int i = ph * (RPP / 8) + ii;
+              if (!(fl[i] & 1)) continue;
+              const float4 acc4 = *reinterpret_cast<const float4*>(&tile[(ii * 8 + sub) * PITCH + cl]);
+              float4 bv = bv0;
+              if (p.bias && d.bias_n_mod) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (long long)((fl[i] >> 1) % d.bias_n_mod) * d.Cout + col));
+              float4 o = make_float4(acc4.x + bv.x + ra[i].x + rb[i].x, acc4.y + bv.y + ra[i].y + rb[i].y,
+                                     acc4.z + bv.z + ra[i].z + rb[i].z, acc4.w + bv.w + ra[i].w + rb[i].w);
+              const long long eo = yo[i] + col;
+              if (GM == 1 || p.splits > 1) {                     // taps / K splits race on an output row: red.add (fp32 only)
+                tt_red_add_v4(p.y + eo, o.x, o.y, o.z, o.w);
+              } else {
+                o = make_float4(tt_act(o.x, d.act), tt_act(o.y, d.act), tt_act(o.z, d.act), tt_act(o.w, d.act));
+                if (p.y) *reinterpret_cast<float4*>(p.y + eo) = o;
+                if (p.ys) {
+                  uint2 hi, lo;
+                  split4(o, hi, lo, sat);
+                  *reinterpret_cast<uint2*>(p.ys + eo) = hi;
+                  *reinterpret_cast<uint2*>(p.ys + p.ys_plane + eo) = lo;
+                }
               }
             }
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
     }
     if (sat) atomicAdd(&g_f16s_saturated, 1u);
   }
@@ -816,13 +836,14 @@ int num_sms_cached() {
 }
 constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;
 
-template <int BN, int STAGES, int GATHER, bool PAIR>
+template <int BN, int STAGES, int GATHER, bool PAIR, int EW = 8>
 cudaError_t launch_f16s_v(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
   constexpr int smem = STAGES * (2 * BM * KE * 2 + 2 * BN * KE * 2) + 1024 + EPI_BYTES;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
   cfg.dynamicSmemBytes = smem;
-  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR>, ma, mb, a);
+  cfg.blockDim = dim3(64 + 32 * EW);
+  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW>, ma, mb, a);
 }
 // work items / grid for `tiles` M tiles; debug bit 0x100000 selects the unpaired variant
 template <int BN, int STAGES, int GATHER>
@@ -834,6 +855,11 @@ cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CU
   const long long max_items = num_sms / cl;
   cfg.gridDim = dim3((unsigned)(cl * (items < max_items ? items : max_items)));
   cfg.attrs[0].val.clusterDim.x = cl;
+  // 16 epilogue warps (dense BN = 128 tiles): twice the warps hiding the store / residual latencies of the short-K layers, where the
+  // epilogue sets the pace (debug bit 0x400000 selects them)
+  if constexpr (GATHER == 0 && BN == 128) {
+    if (pair && (g_tt_debug & 0x400000) && !a.res2 && !a.res2_s) return launch_f16s_v<BN, STAGES, GATHER, true, 16>(cfg, ma, mb, a);
+  }
   return pair ? launch_f16s_v<BN, STAGES, GATHER, true>(cfg, ma, mb, a) : launch_f16s_v<BN, STAGES, GATHER, false>(cfg, ma, mb, a);
 }
 
