@@ -858,7 +858,7 @@ cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CU
   // 16 epilogue warps for the 1x1 layers (dense BN = 128 tiles): with one to four K stages per tile the epilogue sets the pace, and
   // twice the warps hide its store / residual latencies (measured +17..22 % on 64->256 / 256->256 @112x224, +7 % on 2048->512); the
   // 3x3 trunk layers keep 8 (256->256 @112x224: -6 % with 16).  Debug bit 0x400000 turns the variant off.
-  if constexpr (GATHER == 0 && BN == 128) {
+  if constexpr (GATHER == 0) {
     if (pair && a.d.KH * a.d.KW == 1 && !(g_tt_debug & 0x400000) && !a.res2 && !a.res2_s) return launch_f16s_v<BN, STAGES, GATHER, true, 16>(cfg, ma, mb, a);
   }
   return pair ? launch_f16s_v<BN, STAGES, GATHER, true>(cfg, ma, mb, a) : launch_f16s_v<BN, STAGES, GATHER, false>(cfg, ma, mb, a);

@@ -152,17 +152,20 @@ class LSS(nn.Module):
                 outs.append(x)
         return outs
 
-    def _pafpn(self, c):
+    def _pafpn(self, c, dst=None):
+        """dst: optional list of 4 FMaps (or None entries) the final outputs are written into — the skip slices of the UNet's concat
+        buffers, so that the skip connection costs no copy (lss.py:254-256 concatenates them)."""
         e, w = self.eng, self.w
+        dst = dst or [None] * 4
         lat = [None] * 4
         lat[3] = e.conv(c[3], w['lateral_convs'][3], name='fpn.lat3', fmt='s')
         for i in (2, 1, 0):                                            # top-down, nearest x2 fused as residual
             lat[i] = e.conv(c[i], w['lateral_convs'][i], name=f'fpn.lat{i}', res=lat[i + 1], res_mode=lib.RES_UP2, fmt='s')
-        inter = [e.conv(lat[i], w['fpn_convs'][i], name=f'fpn.int{i}', pad=1, fmt='s') for i in range(4)]
+        inter = [e.conv(lat[i], w['fpn_convs'][i], out=dst[0] if i == 0 else None, name=f'fpn.int{i}', pad=1, fmt='s') for i in range(4)]
         for i in range(3):                                             # bottom-up: inter[i+1] += down(inter[i])
             inter[i + 1] = e.conv(inter[i], w['downsample_convs'][i], out=inter[i + 1], name=f'fpn.down{i}', stride=2,
                                   pad=1, res=inter[i + 1])
-        outs = [inter[0]] + [e.conv(inter[i], w['pafpn_convs'][i - 1], name=f'fpn.out{i}', pad=1, fmt='s') for i in (1, 2, 3)]
+        outs = [inter[0]] + [e.conv(inter[i], w['pafpn_convs'][i - 1], out=dst[i], name=f'fpn.out{i}', pad=1, fmt='s') for i in (1, 2, 3)]
         return outs
 
     def _se_vec(self, m, which):
@@ -211,7 +214,8 @@ class LSS(nn.Module):
         for i in range(2):
             for j in range(2):
                 e.conv(x, ups[i][j], out=up, name=f'{name}.up{i}{j}', scatter=(2, i, 2, j))
-        e.copy_cols(skip, cat.slice(cu, skip.C))
+        if not (skip.t is cat.t and skip.s is cat.s and skip.coff == cu):   # else the PAFPN wrote the skip straight into the slice
+            e.copy_cols(skip, cat.slice(cu, skip.C))
         return cat
 
     def _unet(self, f):
@@ -257,7 +261,13 @@ class LSS(nn.Module):
             pb = e.nchw_to_nhwc_padded(im, 'img.nhwc', 4, 3, 3, 3, 5)
             x = e.conv(FMap(pb, B * N, H0 + 6, W0, 32, ld=4), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
                        x_hstride=Wp * 4, x_nstride=(H0 + 6) * Wp * 4)
-        fpn = self._pafpn(self._backbone(x))
+        c = self._backbone(x)
+        # the UNet's concat buffers exist before the PAFPN runs: its outputs 0..2 ARE the skip halves of cat2 / cat3 / cat4
+        skips = []
+        for lvl, (nm, cu) in enumerate((('un.cat2', w['u2_up'][0][0].Cout), ('un.cat3', w['u3_up'][0][0].Cout), ('un.cat4', w['u4_up'][0][0].Cout))):
+            ci = c[lvl]
+            skips.append(e.fmap(nm, ci.N, ci.H, ci.W, cu + 256, fmt='s').slice(cu, 256))
+        fpn = self._pafpn(c, skips + [None])
         src = e.conv(fpn[2], w['neck_conv'], name='img_feats', fmt='s')
         mlp_in = e.wrap(e.static('in.mlp_in').view(B * N, 1, 1, 24))
         merge_in = e.fmap('merge_in', B * N, src.H, src.W, self.output_channels + 128, fmt='s')
