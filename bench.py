@@ -308,11 +308,15 @@ def main():
     model.eng.prof = None
     tensor_peak, hbm_peak, peak_src = load_peaks()
     traffic, traffic_note = None, None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_tc_full.json')
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r2_kernels_b1.json')
     if os.path.exists(tpath):                                    # DRAM bytes per launch from the committed ncu --set full capture
         tj = json.load(open(tpath))
-        traffic = tj['dram_bytes_per_launch_mean']
-        traffic_note = 'bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches: %s' % (len(tj['launches']), tj['source'])
+        dom = [l for l in tj['launches'] if 'conv_f16s_kernel' in l['kernel'] and ', 0, ' in l['kernel'] and l['dur_ns'] >= 100e3]
+        if dom:
+            traffic = sum(l['dram_bytes'] for l in dom) / len(dom)
+            traffic_note = ('bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d dense conv_f16s launches of >= 100 us '
+                            'in the committed capture (%s: one eager B=1 forward, tools/ncu_ops.py; per-launch rows in profiles/r2_kernels_b1.md)'
+                            % (len(dom), tj['source']))
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
     # ---- closed-loop latency (configs[1]): one frame per forward through the same model, graph replay
@@ -344,7 +348,7 @@ def main():
                        'f16s': 'f32 (operands as scaled-split fp16 pairs hi + lo/2048 = 22 mantissa bits, 3 tensor-core products, fp32 accumulate)'}[args.conv], gpu_launches=launches, clocks=summarize_clocks(samples),
                 e2e={'value': frames / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                      'd2h_bytes_per_step': B * 6 * 4 * 2 * 4},
-                roofline={'bound': 'tensor', 'kernel': 'conv_igemm (implicit-GEMM conv / linear family)',
+                roofline={'bound': 'tensor', 'kernel': 'conv_f16s_kernel (implicit-GEMM conv / linear / sparse-conv family on tcgen05, scaled-split fp16 operands; + the few SIMT fallbacks)',
                           'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
                           'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src, 'launches_per_step': n_conv,
                           'kernel_ms_per_step': conv_ms, 'kernel_share_of_step': conv_ms / eager_step_ms,
