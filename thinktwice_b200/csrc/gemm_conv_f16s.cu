@@ -750,31 +750,22 @@ __global__ void __launch_bounds__(256) pointwise_f16s_kernel(const __half* __res
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = (bias && co0 + i < Cout) ? bias[co0 + i] : 0.f;
   __syncthreads();
   bool sat = false;
-  // two pixels per thread (pix, pix + stride/2 ... here: pix and pix + half): every broadcast weight read feeds 8 FFMAs instead of 4
-  const long long half = (npix + 1) / 2;
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < half; pix += (long long)gridDim.x * blockDim.x) {
-    const long long pixb = pix + half;
-    const bool two = pixb < npix;
-    float acc[2][COUT];
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    float acc[COUT];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) { acc[0][co] = bs[co]; acc[1][co] = bs[co]; }
-    const __half* xr0 = xs + pix * x_ld;
-    const __half* xr1 = xs + (two ? pixb : pix) * x_ld;
+    for (int co = 0; co < COUT; ++co) acc[co] = bs[co];
+    const __half* xr = xs + pix * x_ld;
     for (int k0 = 0; k0 < K8; k0 += 8) {
-      float xv[2][8];
+      const uint4 h = *reinterpret_cast<const uint4*>(xr + k0);
+      const uint4 l = *reinterpret_cast<const uint4*>(xr + xs_plane + k0);
+      const __half2* hp = reinterpret_cast<const __half2*>(&h);
+      const __half2* lp = reinterpret_cast<const __half2*>(&l);
+      float xv[8];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const __half* xr = t ? xr1 : xr0;
-        const uint4 h = *reinterpret_cast<const uint4*>(xr + k0);
-        const uint4 l = *reinterpret_cast<const uint4*>(xr + xs_plane + k0);
-        const __half2* hp = reinterpret_cast<const __half2*>(&h);
-        const __half2* lp = reinterpret_cast<const __half2*>(&l);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = __half22float2(hp[j]), b = __half22float2(lp[j]);
-          xv[t][2 * j] = fmaf(b.x, LO_INV, a.x);
-          xv[t][2 * j + 1] = fmaf(b.y, LO_INV, a.y);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(hp[j]), b = __half22float2(lp[j]);
+        xv[2 * j] = fmaf(b.x, LO_INV, a.x);
+        xv[2 * j + 1] = fmaf(b.y, LO_INV, a.y);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -782,31 +773,23 @@ __global__ void __launch_bounds__(256) pointwise_f16s_kernel(const __half* __res
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; ++c4) {
           const float4 wv = wr[c4];                                    // same address in every lane: shared-memory broadcast
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            acc[t][4 * c4] = fmaf(xv[t][j], wv.x, acc[t][4 * c4]);
-            acc[t][4 * c4 + 1] = fmaf(xv[t][j], wv.y, acc[t][4 * c4 + 1]);
-            acc[t][4 * c4 + 2] = fmaf(xv[t][j], wv.z, acc[t][4 * c4 + 2]);
-            acc[t][4 * c4 + 3] = fmaf(xv[t][j], wv.w, acc[t][4 * c4 + 3]);
-          }
+          acc[4 * c4] = fmaf(xv[j], wv.x, acc[4 * c4]);
+          acc[4 * c4 + 1] = fmaf(xv[j], wv.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(xv[j], wv.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(xv[j], wv.w, acc[4 * c4 + 3]);
         }
       }
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (t && !two) break;
-      const long long po = (t ? pixb : pix) * y_ld + co0;
-#pragma unroll
-      for (int c4 = 0; c4 < COUT / 4; ++c4) {
-        if (co0 + 4 * c4 >= Cout) break;
-        const float4 o = make_float4(tt_act(acc[t][4 * c4], act), tt_act(acc[t][4 * c4 + 1], act), tt_act(acc[t][4 * c4 + 2], act), tt_act(acc[t][4 * c4 + 3], act));
-        if (y) *reinterpret_cast<float4*>(y + po + 4 * c4) = o;
-        if (ys) {
-          uint2 hi, lo;
-          split4(o, hi, lo, sat);
-          *reinterpret_cast<uint2*>(ys + po + 4 * c4) = hi;
-          *reinterpret_cast<uint2*>(ys + ys_plane + po + 4 * c4) = lo;
-        }
+    for (int c4 = 0; c4 < COUT / 4; ++c4) {
+      if (co0 + 4 * c4 >= Cout) break;
+      const float4 o = make_float4(tt_act(acc[4 * c4], act), tt_act(acc[4 * c4 + 1], act), tt_act(acc[4 * c4 + 2], act), tt_act(acc[4 * c4 + 3], act));
+      if (y) *reinterpret_cast<float4*>(y + pix * y_ld + co0 + 4 * c4) = o;
+      if (ys) {
+        uint2 hi, lo;
+        split4(o, hi, lo, sat);
+        *reinterpret_cast<uint2*>(ys + pix * y_ld + co0 + 4 * c4) = hi;
+        *reinterpret_cast<uint2*>(ys + ys_plane + pix * y_ld + co0 + 4 * c4) = lo;
       }
     }
   }
@@ -968,8 +951,7 @@ int tt_pointwise_f16s(const tt_conv_desc* d, const tt_f16s_io* io, const float* 
   }
   const long long npix = (long long)d->N * d->H * d->W;
   if (npix == 0) return TT_OK;
-  const long long nthr = (npix + 1) / 2;                          // two pixels per thread
-  const int nb = (int)((nthr + 255) / 256 > 148 * 8 ? 148 * 8 : (nthr + 255) / 256);
+  const int nb = (int)((npix + 255) / 256 > 148 * 8 ? 148 * 8 : (npix + 255) / 256);
   const __half* xs = static_cast<const __half*>(io->x_split);
   __half* ys = static_cast<__half*>(io->y_split);
   float* y = io->y ? io->y + d->y_coff : nullptr;
