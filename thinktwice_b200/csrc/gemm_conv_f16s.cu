@@ -740,8 +740,10 @@ __global__ void __launch_bounds__(256) pointwise_f16s_kernel(const __half* __res
                                                               const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                                               float* __restrict__ y, __half* __restrict__ ys, long long ys_plane, int y_ld,
                                                               int act, long long npix, int co0) {
+  constexpr int RP = COUT * 2 + 16;                                  // staging row pitch in bytes (+16: conflict-free 16-byte accesses)
   __shared__ __align__(16) float ws[64 * COUT];                      // [k][co0 + co], rows beyond Cin / columns beyond Cout are zero
   __shared__ float bs[COUT];
+  __shared__ __align__(16) uint8_t stage[8][32 * RP];                // per warp: 32 pixels x COUT halves (one plane at a time)
   const int K8 = (Cin + 7) / 8 * 8;
   for (int i = threadIdx.x; i < 64 * COUT; i += blockDim.x) {
     const int k = i / COUT, co = i - k * COUT;
@@ -749,12 +751,16 @@ __global__ void __launch_bounds__(256) pointwise_f16s_kernel(const __half* __res
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = (bias && co0 + i < Cout) ? bias[co0 + i] : 0.f;
   __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool sat = false;
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+  // whole warps walk 32 consecutive pixels at a time (the tail warp clamps its loads and predicates its stores)
+  for (long long base = (blockIdx.x * (long long)(blockDim.x >> 5) + warp) * 32; base < npix; base += (long long)gridDim.x * blockDim.x) {
+    const long long pix = base + lane;
+    const bool live = pix < npix;
     float acc[COUT];
 #pragma unroll
     for (int co = 0; co < COUT; ++co) acc[co] = bs[co];
-    const __half* xr = xs + pix * x_ld;
+    const __half* xr = xs + (live ? pix : npix - 1) * x_ld;
     for (int k0 = 0; k0 < K8; k0 += 8) {
       const uint4 h = *reinterpret_cast<const uint4*>(xr + k0);
       const uint4 l = *reinterpret_cast<const uint4*>(xr + xs_plane + k0);
@@ -780,16 +786,33 @@ __global__ void __launch_bounds__(256) pointwise_f16s_kernel(const __half* __res
         }
       }
     }
+    // ---- outputs.  fp32 rows: direct 16-byte stores.  Planes: this lane's COUT halves go through a per-warp staging buffer so that the
+    // global stores are 16 bytes per lane with 4 (COUT 32) / 2 (COUT 16) lanes on one pixel row: full 32-byte sectors instead of 8-byte shards
+    uint2 hv[COUT / 4], lv[COUT / 4];
 #pragma unroll
     for (int c4 = 0; c4 < COUT / 4; ++c4) {
-      if (co0 + 4 * c4 >= Cout) break;
       const float4 o = make_float4(tt_act(acc[4 * c4], act), tt_act(acc[4 * c4 + 1], act), tt_act(acc[4 * c4 + 2], act), tt_act(acc[4 * c4 + 3], act));
-      if (y) *reinterpret_cast<float4*>(y + pix * y_ld + co0 + 4 * c4) = o;
-      if (ys) {
-        uint2 hi, lo;
-        split4(o, hi, lo, sat);
-        *reinterpret_cast<uint2*>(ys + pix * y_ld + co0 + 4 * c4) = hi;
-        *reinterpret_cast<uint2*>(ys + ys_plane + pix * y_ld + co0 + 4 * c4) = lo;
+      if (y && live && co0 + 4 * c4 < Cout) *reinterpret_cast<float4*>(y + pix * y_ld + co0 + 4 * c4) = o;
+      split4(o, hv[c4], lv[c4], sat);
+    }
+    if (ys) {
+      constexpr int LPR = COUT / 8;                                    // lanes per pixel row (16-byte chunks of COUT halves)
+      constexpr int RPI = 32 / LPR;                                    // pixel rows per store instruction
+      const int chunk = lane % LPR, rsub = lane / LPR;
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        __syncwarp();
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) *reinterpret_cast<uint2*>(&stage[warp][lane * RP + c4 * 8]) = pl ? lv[c4] : hv[c4];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 32 / RPI; ++it) {
+          const int prow = it * RPI + rsub;
+          const long long gp = base + prow;
+          if (gp < npix && co0 + chunk * 8 < Cout)
+            *reinterpret_cast<uint4*>(ys + (pl ? ys_plane : 0) + gp * y_ld + co0 + chunk * 8) =
+                *reinterpret_cast<const uint4*>(&stage[warp][prow * RP + chunk * 16]);
+        }
       }
     }
   }
@@ -952,6 +975,7 @@ int tt_pointwise_f16s(const tt_conv_desc* d, const tt_f16s_io* io, const float* 
   const long long npix = (long long)d->N * d->H * d->W;
   if (npix == 0) return TT_OK;
   const int nb = (int)((npix + 255) / 256 > 148 * 8 ? 148 * 8 : (npix + 255) / 256);
+  TT_REQUIRE(d->Cout % 8 == 0 || !io->y_split, "tt_pointwise_f16s", "plane output needs Cout % 8 == 0");
   const __half* xs = static_cast<const __half*>(io->x_split);
   __half* ys = static_cast<__half*>(io->y_split);
   float* y = io->y ? io->y + d->y_coff : nullptr;
