@@ -122,3 +122,34 @@ def test_inputs_that_change_shape_between_calls_are_not_served_from_stale_buffer
     # the staged cloud is padded to the bucket with points the voxeliser drops
     pb = m.eng.static('in.points')
     assert pb.shape[1] % 8192 == 0 and float(pb[0, -1, 0]) > 1e29
+
+
+def test_streaming_bev_cache_reproduces_the_full_forward_in_closed_loop(emulated):
+    """with a static rig the history sweep's BEV (previous images, CURRENT key-frame matrices, lss.py:712-716) is the
+    key-frame BEV of the previous tick.  Three consecutive ticks of one stream: cached forwards == full forwards == oracle."""
+    from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.registry import build_model
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    cfg.model['img_encoder']['queue_len'] = 2
+    cfg.model['train_cfg']['queue_length'] = 2
+    o = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'})
+    init_oracle_weights(o, 2)
+    ticks = [make_batch(cfg, 1, seed=30 + t, num_points=600) for t in range(3)]
+    for t in (1, 2):                                                 # a stream: the history frame of tick t is the key frame of tick t - 1
+        ticks[t]['img'][:, 0] = ticks[t - 1]['img'][:, 1]
+    calibrate_bn(o, ticks[0])
+    m = build_model(cfg.model)
+    m.load_state_dict(o.state_dict())
+    m.prepare('cpu', impl=4)
+    m.enable_streaming_bev_cache()
+    for t, b in enumerate(ticks):
+        assert m.img_encoder.cache_ready(1) == (t > 0)
+        with torch.no_grad():
+            ref = o.forward_inference(b)
+        pred = m.forward_inference(b)
+        for k in ('pred_wp', 'mu_branches', 'pred_speed'):
+            assert rel(pred[k], ref[k]) < 5e-4, (t, k)
+    m.reset_stream()
+    assert not m.img_encoder.cache_ready(1)

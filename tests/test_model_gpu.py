@@ -191,3 +191,35 @@ def test_throughput_config_b32_encoder_is_batch_invariant_and_decoder_matches_or
         assert relerr(c1['bev'].nchw(), keep32['cam_bev'][j:j + 1]) < 5e-4, j
         assert relerr(c1['seg'].nchw(), keep32['seg'][j * 4:(j + 1) * 4]) < 5e-4, j
         assert relerr(e.static_named('lidar.out.at').permute(0, 3, 1, 2), keep32['lidar'][j:j + 1]) < 5e-4, j
+
+
+def test_streaming_bev_cache_equals_the_full_forward_on_a_consecutive_stream():
+    """SURVEY §8f f2 (closed loop): the history sweep's BEV is the previous tick's key-frame BEV.  Three consecutive ticks with the
+    cache (eager, then as CUDA-graph replays) against full forwards of the same ticks."""
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.registry import build_model
+    from thinktwice_b200.synthetic import make_batch
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    cfg.model['img_encoder']['queue_len'] = 2
+    cfg.model['train_cfg']['queue_length'] = 2
+    from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
+    oracle = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'})
+    init_oracle_weights(oracle, 4)
+    ticks = [make_batch(cfg, 1, seed=40 + t, num_points=1500) for t in range(4)]
+    for t in range(1, 4):
+        ticks[t]['img'][:, 0] = ticks[t - 1]['img'][:, 1]
+    calibrate_bn(oracle, ticks[0])
+    model = build_model(cfg.model)
+    model.load_state_dict(oracle.state_dict())
+    model.prepare('cuda:0')
+    full = [{k: model.forward_inference(b)[k].clone() for k in ('pred_wp', 'mu_branches', 'refine_BEV_feature')} for b in ticks]
+    for use_graph in (False, True):
+        model.enable_streaming_bev_cache()
+        if use_graph:
+            model.enable_cuda_graph()
+        for t, b in enumerate(ticks):
+            pred = model.forward_inference(b)
+            for k, v in full[t].items():
+                assert relerr(pred[k], v) < 1e-4, (use_graph, t, k)
+        model.use_graph = False
+    assert model.f16s_saturations() == 0

@@ -180,7 +180,7 @@ class EncoderDecoder(nn.Module):
         self.decoder.stage(lidar2img, ida)
         return (B, T, N, tuple(img.shape), cap)
 
-    def _device_forward(self):
+    def _device_forward(self, warm=False):
         """Device half: extract_sensor_feat (framework:238-250) + get_fusion_feat + decoder, kernels only."""
         e = self.eng
         # the LiDAR encoder (small, latency-bound sparse kernels) runs on a side stream beside the camera encoder
@@ -189,7 +189,7 @@ class EncoderDecoder(nn.Module):
         with e.side_branch() as side:
             lidar = self.lidar_encoder(e.static('in.points'))
         e.mark('lidar_encoder')
-        cam = self.img_encoder.forward_device(e.static('in.img'))
+        cam = self.img_encoder.forward_device(e.static('in.img'), warm)
         cam['bev'] = e.anti_transpose(cam['bev'], 'cam.bev.at')     # rot90(flip): match the Roach BEV
         st = e.static('in.state')
         m = e.linear(e.wrap(st.view(-1, 1, 1, 12)), self.w['meas0'], name='meas.h', act=ACT_RELU)
@@ -231,6 +231,7 @@ class EncoderDecoder(nn.Module):
         e.bufs.clear(); e.bufs.update(keep)
         e.cur.clear(); e.last_buf.clear(); e.conv_ws.clear(); e._ws_retired.clear(); e._scratch.clear()
         self.last_cam_feat = None
+        self.img_encoder.reset_stream()
         if e.device.type == 'cuda':
             torch.cuda.synchronize()
             torch.cuda.empty_cache()
@@ -244,19 +245,35 @@ class EncoderDecoder(nn.Module):
         if getattr(self, '_arena_B', B_now) != B_now:
             self.release_buffers()                                 # one arena at a time: another batch size starts from scratch
         self._arena_B = B_now
-        key = self.stage(batch)
+        warm = self.img_encoder.cache_ready(B_now)                 # streaming BEV cache: the previous tick left its key-frame BEV behind
+        key = self.stage(batch) + (warm,)
         if not getattr(self, 'use_graph', False):
-            return self._own(self._device_forward())
-        g = self._graphs.get(key)
-        if g is None:
-            self._device_forward()                                 # eager warm-up: allocates all persistent buffers
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                pred = self._device_forward()
-            g = self._graphs[key] = (graph, pred)
-        g[0].replay()
-        return self._own(g[1].fresh())
+            pred = self._own(self._device_forward(warm))
+        else:
+            g = self._graphs.get(key)
+            if g is None:
+                self._device_forward(warm)                         # eager warm-up: allocates all persistent buffers
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    pred = self._device_forward(warm)
+                g = self._graphs[key] = (graph, pred)
+            g[0].replay()
+            pred = self._own(g[1].fresh())
+        if self.img_encoder.stream_cache:
+            self.img_encoder._cache_B = B_now
+        return pred
+
+    def enable_streaming_bev_cache(self, flag=True):
+        """closed-loop mode: reuse the previous forward's key-frame BEV as this forward's history-sweep BEV instead of
+        re-encoding the history images (lss.py:712-716 applies the CURRENT key-frame matrices to them: identical for a static rig).
+        The caller vouches that forwards are consecutive ticks of one stream; call reset_stream() when a new episode starts."""
+        self.img_encoder.stream_cache = bool(flag)
+        self.img_encoder.reset_stream()
+        return self
+
+    def reset_stream(self):
+        self.img_encoder.reset_stream()
 
     SMALL_OUTPUTS = ('pred_speed', 'pred_value_traj', 'pred_features_traj', 'pred_value_ctrl', 'pred_features_ctrl', 'pred_wp',
                      'mu_branches', 'sigma_branches', 'future_mu', 'future_sigma')
