@@ -223,3 +223,39 @@ def test_streaming_bev_cache_equals_the_full_forward_on_a_consecutive_stream():
                 assert relerr(pred[k], v) < 1e-4, (use_graph, t, k)
         model.use_graph = False
     assert model.f16s_saturations() == 0
+
+
+def test_pipelined_host_input_forward_equals_the_single_stream_forward():
+    """host-resident batch (the agent / bench e2e case): uploads ordered by first use and overlapped with the kernels on three
+    streams (EncoderDecoder._pipelined_forward), eagerly and as three CUDA graphs, against the same batch resident on the device
+    run on one stream; different frames on consecutive calls so that a stale input buffer or a missing stream dependency shows."""
+    from thinktwice_b200.config import Config, PLUMBING_CONFIG
+    from thinktwice_b200.registry import build_model
+    from thinktwice_b200.synthetic import make_batch
+    from oracle.model import EncoderDecoder as Oracle, calibrate_bn, init_oracle_weights
+    cfg = Config.fromfile(PLUMBING_CONFIG)
+    cfg.model['img_encoder']['queue_len'] = 2
+    cfg.model['train_cfg']['queue_length'] = 2
+    oracle = Oracle(**{k: v for k, v in cfg.model.items() if k != 'type'})
+    init_oracle_weights(oracle, 6)
+    frames = [make_batch(cfg, 2, seed=60 + t, num_points=1500) for t in range(3)]
+    calibrate_bn(oracle, frames[0])
+    model = build_model(cfg.model)
+    model.load_state_dict(oracle.state_dict())
+    model.prepare('cuda:0')
+    keys = ('pred_wp', 'mu_branches', 'refine_BEV_feature', 'pred_speed')
+    resident = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()} for b in frames]
+    want = [{k: model.forward_inference(b)[k].clone() for k in keys} for b in resident]
+    assert not any(k[0] == 'pipe' for k in getattr(model, '_graphs', {}))
+    pinned = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in frames]
+    for use_graph in (False, True):
+        if use_graph:
+            model.enable_cuda_graph()
+        for rnd in range(2):
+            for t, b in enumerate(pinned):
+                pred = model.forward_inference(b)
+                for k, v in want[t].items():
+                    assert relerr(pred[k], v) < 1e-4, (use_graph, rnd, t, k)
+    assert any(k[0] == 'pipe' for k in model._graphs)              # the graph rounds really took the three-graph path
+    model.use_graph = False
+    assert model.f16s_saturations() == 0

@@ -151,7 +151,8 @@ class EncoderDecoder(nn.Module):
     # ------------------------------------------------------------------ forward (framework:194-210, 238-250)
     def stage(self, batch):
         """Host half of forward_inference: everything that touches host data (state vector, img_metas matrices) is
-        computed here and uploaded into static device buffers, so the device half is a fixed launch sequence."""
+        computed here and uploaded into static device buffers, so the device half is a fixed launch sequence.  The images —
+        the bulk of the input bytes — are staged separately (_stage_sweep), sweep by sweep."""
         e = self.eng
         img = batch['img']
         if img.dim() == 5:
@@ -160,7 +161,6 @@ class EncoderDecoder(nn.Module):
         speed = batch['speed'].to(dtype=torch.float32).view(-1, 1) / 12.
         st = torch.cat([speed, batch['target_point'].to(torch.float32), batch['target_command'].to(torch.float32)], -1)
         e.upload('in.state', torch.cat([st, st.new_zeros(B, 3)], 1).contiguous())      # 9 -> 12 columns (vector loads)
-        e.upload('in.img', img.to(torch.float32))
         # LiDAR points: the point count changes every tick in closed loop (thinktwice_agent.py:340-352).  The cloud is
         # staged into a buffer whose capacity is the count rounded up to POINT_BUCKET, the tail filled with
         # out-of-range points (dropped by the voxeliser exactly like any point outside point_cloud_range), so that one
@@ -178,23 +178,39 @@ class EncoderDecoder(nn.Module):
         e.cur['in.points'] = pb
         lidar2img, ida = self.img_encoder.stage(batch['img_metas'], B, T, N)
         self.decoder.stage(lidar2img, ida)
-        return (B, T, N, tuple(img.shape), cap)
+        self._imgs = [e.buf(f'in.img.{t}', (B,) + tuple(img.shape[2:])) for t in range(T)]
+        return img, (B, T, N, tuple(img.shape), cap)
 
-    def _device_forward(self, warm=False):
-        """Device half: extract_sensor_feat (framework:238-250) + get_fusion_feat + decoder, kernels only."""
+    def _stage_sweep(self, img, t):
+        """images of sweep t of `img` (B, T, N, 3, H, W; host or device, any float / integer dtype) into the sweep's static
+        device buffer, on the current stream.  Host tensors travel frame by frame: each (N, 3, H, W) block is contiguous, so a
+        pinned source goes out as plain asynchronous copies (a strided (B, ...) slice would be gathered on the CPU first)."""
+        dst = self._imgs[t]
+        if img.is_cuda:
+            dst.copy_(img[:, t], non_blocking=True)
+        else:
+            for b in range(img.shape[0]):
+                dst[b].copy_(img[b, t], non_blocking=True)
+
+    # The device half in three phases, by the inputs they need.  One stream runs them back to back (_device_forward); with host
+    # inputs they are pipelined against the uploads (_pipelined_forward).
+    def _phase_lidar(self):
+        return self.lidar_encoder(self.eng.static('in.points'))     # needs the points only
+
+    def _phase_history(self, warm=False):
+        self.img_encoder.history_device(self._imgs, warm)          # needs the history sweeps' images (none when `warm`)
+
+    def _phase_key(self, lidar, join=None):
+        """key-frame sweep + extract_sensor_feat's tail (framework:238-250) + get_fusion_feat + decoder.  join(): called right
+        before the first kernel that reads the LiDAR branch's output."""
         e = self.eng
-        # the LiDAR encoder (small, latency-bound sparse kernels) runs on a side stream beside the camera encoder
-        # (large tensor-core kernels): the two branches only meet in get_fusion_feat
-        e.mark('start')
-        with e.side_branch() as side:
-            lidar = self.lidar_encoder(e.static('in.points'))
-        e.mark('lidar_encoder')
-        cam = self.img_encoder.forward_device(e.static('in.img'), warm)
+        cam = self.img_encoder.key_device(self._imgs)
         cam['bev'] = e.anti_transpose(cam['bev'], 'cam.bev.at')     # rot90(flip): match the Roach BEV
         st = e.static('in.state')
         m = e.linear(e.wrap(st.view(-1, 1, 1, 12)), self.w['meas0'], name='meas.h', act=ACT_RELU)
         meas = e.linear(m, self.w['meas2'], name='meas', act=ACT_RELU)
-        side.join()
+        if join is not None:
+            join()
         e.mark('camera_encoder')
         flat, bev32, mid, lidar_hi = self.get_fusion_feat(cam['bev'], lidar[0])
         e.mark('bev_fusion')
@@ -202,6 +218,92 @@ class EncoderDecoder(nn.Module):
         e.mark('decoder')
         self.last_cam_feat = cam                                   # cam['seg'] etc. for parity checks
         return pred
+
+    def _device_forward(self, warm=False):
+        """Device half on ONE launching stream, kernels only (every input already staged): capturable as a single CUDA graph."""
+        e = self.eng
+        # the LiDAR encoder (small, latency-bound sparse kernels) runs on a side stream beside the camera encoder
+        # (large tensor-core kernels): the two branches only meet in get_fusion_feat
+        e.mark('start')
+        with e.side_branch() as side:
+            lidar = self._phase_lidar()
+        e.mark('lidar_encoder')
+        self._phase_history(warm)
+        return self._phase_key(lidar, side.join)
+
+    # ------------------------------------------------------------------ pipelined forward (host inputs)
+    # The batch arrives in HOST memory (thinktwice_agent.py:452-454 moves it tensor by tensor; bench.py's e2e leg hands over pinned
+    # tensors): 39 MB of images per frame, 1.26 GB at B = 32 — serial with the forward that is 6 % of the step.  The phases above
+    # need their inputs at different times, so the uploads are ordered by first use and overlapped with the kernels:
+    #   main stream : state / matrices / points | history images | history sweeps ............ | key sweep + fusion + decoder
+    #   side stream :                            | LiDAR encoder (starts under the image upload) ...........|
+    #   copy stream :                                             | key-frame images (under the history sweeps) |
+    # The three kernel groups are three CUDA graphs when graph replay is on (a graph cannot wait for an outside event mid-way).
+    def _pipelined_forward(self, img, key):
+        e = self.eng
+        T = img.shape[1]
+        main = torch.cuda.current_stream()
+        if e._side is None:
+            e._side = torch.cuda.Stream(device=e.device)
+        if e._copy is None:
+            e._copy = torch.cuda.Stream(device=e.device)
+        side, copy = e._side, e._copy
+        graphs = self._graphs.get(('pipe',) + key) if getattr(self, 'use_graph', False) else None
+
+        def run(name, fn):
+            if graphs is None:
+                return fn()
+            graphs[name][0].replay()
+            return graphs[name][1]
+
+        ev_small = torch.cuda.Event()
+        ev_small.record(main)                                      # state, matrices, points are on their way
+        side.wait_event(ev_small)
+        with torch.cuda.stream(side):
+            e.lane = 1
+            try:
+                lidar = run('lidar', self._phase_lidar)
+            finally:
+                e.lane = 0
+            ev_lidar = torch.cuda.Event()
+            ev_lidar.record(side)
+        for t in range(T - 1):
+            self._stage_sweep(img, t)
+        ev_hist = torch.cuda.Event()
+        ev_hist.record(main)
+        copy.wait_event(ev_hist)                                   # one upload at a time: the history images are needed first
+        with torch.cuda.stream(copy):
+            self._stage_sweep(img, T - 1)
+            ev_key = torch.cuda.Event()
+            ev_key.record(copy)
+        run('history', self._phase_history)
+        main.wait_event(ev_key)
+        main.wait_event(ev_lidar)
+        pred = run('key', lambda: self._phase_key(lidar))
+        # the next forward's uploads (issued on `main` / `copy`) must not overtake this forward's readers of the input buffers
+        ev_done = torch.cuda.Event()
+        ev_done.record(main)
+        copy.wait_event(ev_done)
+        side.wait_event(ev_done)
+        return pred.fresh() if graphs is not None else pred
+
+    def _capture_pipeline(self, key):
+        """three graphs over the arena the eager pass just allocated; captured in program order (the key phase holds the LiDAR
+        phase's output maps), replayed by _pipelined_forward on their own streams."""
+        e, graphs, lidar = self.eng, {}, None
+        for name, lane in (('lidar', 1), ('history', 0), ('key', 0)):
+            g = torch.cuda.CUDAGraph()
+            e.lane = lane
+            try:
+                with torch.cuda.graph(g):
+                    out = (self._phase_lidar() if name == 'lidar' else self._phase_history() if name == 'history'
+                           else self._phase_key(lidar))
+            finally:
+                e.lane = 0
+            if name == 'lidar':
+                lidar = out
+            graphs[name] = (g, out)
+        self._graphs[('pipe',) + key] = graphs
 
     def f16s_saturations(self, reset=True):
         """values the scaled-split fp16 engine had to clamp to +-65504 since the last reset (0 in a healthy network; the fp32
@@ -241,28 +343,46 @@ class EncoderDecoder(nn.Module):
         if self.eng is None:
             self.prepare(batch['img'].device if batch['img'].is_cuda else 'cuda:0')
         self.epoch = 10000
+        e = self.eng
         B_now = batch['img'].shape[0]
         if getattr(self, '_arena_B', B_now) != B_now:
             self.release_buffers()                                 # one arena at a time: another batch size starts from scratch
         self._arena_B = B_now
         warm = self.img_encoder.cache_ready(B_now)                 # streaming BEV cache: the previous tick left its key-frame BEV behind
-        key = self.stage(batch) + (warm,)
-        if not getattr(self, 'use_graph', False):
-            pred = self._own(self._device_forward(warm))
-        else:
-            g = self._graphs.get(key)
-            if g is None:
-                self._device_forward(warm)                         # eager warm-up: allocates all persistent buffers
+        img, key = self.stage(batch)
+        key = key + (warm,)
+        T = img.shape[1]
+        use_graph = getattr(self, 'use_graph', False)
+        # host inputs with a history sweep to hide the uploads behind: pipelined (see _pipelined_forward); otherwise one stream
+        pipelined = (self.pipeline_uploads and not img.is_cuda and T > 1 and not warm and e.device.type == 'cuda' and e.overlap
+                     and e.prof is None and e.marks is None)
+        if pipelined:
+            if use_graph and ('pipe',) + key not in self._graphs:
+                self._pipelined_forward(img, key)                  # eager pass: allocates all persistent buffers
                 torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    pred = self._device_forward(warm)
-                g = self._graphs[key] = (graph, pred)
-            g[0].replay()
-            pred = self._own(g[1].fresh())
+                self._capture_pipeline(key)
+            pred = self._own(self._pipelined_forward(img, key))
+        else:
+            for t in range(0 if not warm else T - 1, T):
+                self._stage_sweep(img, t)
+            if not use_graph:
+                pred = self._own(self._device_forward(warm))
+            else:
+                g = self._graphs.get(key)
+                if g is None:
+                    self._device_forward(warm)                     # eager warm-up: allocates all persistent buffers
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        pred = self._device_forward(warm)
+                    g = self._graphs[key] = (graph, pred)
+                g[0].replay()
+                pred = self._own(g[1].fresh())
         if self.img_encoder.stream_cache:
             self.img_encoder._cache_B = B_now
         return pred
+
+    pipeline_uploads = True       # overlap the image uploads of a host-resident batch with the kernels (_pipelined_forward)
 
     def enable_streaming_bev_cache(self, flag=True):
         """closed-loop mode: reuse the previous forward's key-frame BEV as this forward's history-sweep BEV instead of

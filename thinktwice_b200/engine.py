@@ -126,6 +126,7 @@ class Engine:
         self._scratch, self._tmp_maps = {}, set()
         self.lane = 0               # 0 = main stream; 1 = side stream (independent branch running concurrently)
         self._side = None
+        self._copy = None           # upload stream of the pipelined forward (EncoderDecoder._pipelined_forward)
         self.overlap = True         # run independent branches (side_branch) concurrently
         self.marks = None           # bench.py: list of (segment name, event) recorded by mark() in a serial eager step
         self.tc_min_rows = 512

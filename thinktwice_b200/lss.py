@@ -245,7 +245,7 @@ class LSS(nn.Module):
         # stem (ResNet conv1 7x7 s2 p3 on 3 channels): the image goes channels-last (4 floats / pixel) into a buffer with
         # a physical zero border (3 px top / bottom / left, 5 right), so a tap ROW of 7 px x 4 floats is 28 contiguous
         # floats = one 32-float K slab of a 7x1 conv over 32 "channels" (x_ld = 4 < Cin = 32, row pitch x_hstride)
-        im = imgs.reshape(B * N, *imgs.shape[2:])
+        im = imgs.reshape(B * N, *imgs.shape[2:])                      # (a view: every sweep is its own contiguous buffer)
         H0, W0 = im.shape[2:]
         Wp = W0 + 8
         if e.split:
@@ -318,27 +318,43 @@ class LSS(nn.Module):
     def reset_stream(self):
         self._cache_B = None
 
-    def forward_device(self, img, warm=False):
-        """Device half: img (B, T, N, 3, H, W) fp32 resident on the GPU.  warm: take the history sweep's BEV from the streaming cache."""
-        e = self.eng
-        B, T, N = img.shape[:3]
-        assert T == self.queue_len, 'LSS.queue_len must be set correctly in config!'
+    def _bev_bufs(self, B, T):
+        e, Cb = self.eng, self.output_channels
         X, Y = self.h_vnum[0], self.h_vnum[1]
-        Cb = self.output_channels
         bev_cat = e.fmap('bev_cat', B, Y, X, Cb * T)
         cache = e.fmap('bev.keycache', B, Y, X, Cb) if (self.stream_cache and T == 2) else None
+        return bev_cat, cache
+
+    def history_device(self, imgs, warm=False):
+        """Device half, part 1: the history sweeps (lss.py:710-717) — needs every image but the key frame's.  imgs: one
+        (B, N, 3, H, W) fp32 device tensor per sweep, oldest first, key frame last (entries may be None when `warm`).
+        warm: take the history sweep's BEV from the streaming cache."""
+        e, T, Cb = self.eng, len(imgs), self.output_channels
+        assert T == self.queue_len, 'LSS.queue_len must be set correctly in config!'
+        bev_cat, cache = self._bev_bufs(imgs[-1].shape[0], T)
         # history sweeps first (their buffers are recycled), key frame last so its FPN maps stay live.
         # bev_feature_list = [key, sweep 1, ...] (lss.py:697,717)
         if warm:
             e.copy_cols(cache, bev_cat.slice(Cb, Cb))
         else:
             for s in range(T - 1, 0, -1):
-                self._single_sweep(img[:, T - 1 - s], s, bev_cat.slice(Cb * s, Cb))
-        key = self._single_sweep(img[:, T - 1], 0, bev_cat.slice(0, Cb))
+                self._single_sweep(imgs[T - 1 - s], s, bev_cat.slice(Cb * s, Cb))
+
+    def key_device(self, imgs):
+        """Device half, part 2: the key-frame sweep, then the sweep merge (lss.py:697-724)."""
+        e, T, Cb = self.eng, len(imgs), self.output_channels
+        bev_cat, cache = self._bev_bufs(imgs[-1].shape[0], T)
+        key = self._single_sweep(imgs[-1], 0, bev_cat.slice(0, Cb))
         if cache is not None:
             e.copy_cols(bev_cat.slice(0, Cb), cache)                 # this tick's key-frame BEV is the next tick's history BEV
         bev = e.conv(bev_cat, self.w['sweep_merge'], name='bev', pad=1) if T > 1 else bev_cat
         return dict(bev=bev, seg=key['seg'], depth=key['depth'], fpn_feats=key['fpn_feats'], img_feature=key['img_feature'])
+
+    def forward_device(self, img, warm=False):
+        """Device half: img (B, T, N, 3, H, W) fp32 resident on the GPU, or the list of its T sweeps (B, N, 3, H, W)."""
+        imgs = list(img) if isinstance(img, (list, tuple)) else [img[:, t].contiguous() for t in range(img.shape[1])]
+        self.history_device(imgs, warm)
+        return self.key_device(imgs)
 
     def forward(self, img, img_metas, timestamps=None, is_return_depth=False):
         if img.dim() == 5:

@@ -49,7 +49,7 @@ def main():
     res['lidar_encoder'], lidar = graph_ms(lambda: model.lidar_encoder(e.static('in.points')))
 
     def cam_fn():
-        cam = model.img_encoder.forward_device(e.static('in.img'))
+        cam = model.img_encoder.forward_device(model._imgs)
         cam['bev'] = e.anti_transpose(cam['bev'], 'cam.bev.at')
         st = e.static('in.state')
         m = e.linear(e.wrap(st.view(-1, 1, 1, 12)), model.w['meas0'], name='meas.h', act=ACT_RELU)
