@@ -334,6 +334,56 @@ int tt_look_reduce(const float* rows, int B, int cams, int cap, int C, const int
 int tt_gru_input(const float* wp, const float* ctrl_sp, int t, int T, float* buf, int ld, int B, int HW,
                  tt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (8) agent-side pre-processing: the CPU work between the CARLA sensors and forward_inference.
+ */
+typedef struct {
+  int n_img;            /* images in `raw` (T * N per tick, or B * T * N) */
+  int H, W;             /* raw camera frame (900 x 1600: thinktwice_agent.py:237) */
+  int newH, newW;       /* resize_dims of sample_ida_augmentation (transform.py:264-267): int(H * resize), int(W * resize) */
+  int outH, outW;       /* final_dim = the crop window's size (448 x 896) */
+  int crop_x, crop_y;   /* crop[:2] (transform.py:268-271) */
+  int undistort;        /* cfg["undistort"]: sample the raw frame through map_grid first (transform.py:281-282) */
+  float div;            /* 255 (transform.py:162) */
+  float mean[3], std[3];/* T.Normalize constants (transform.py:144) */
+  int pad_H, pad_W, pad_top, pad_left; /* geometry of the stem-plane output (see tt_image_to_split8); ignored without out_split8 */
+} tt_preproc_desc;
+/* Replaces IDAImageTransform.__call__ + img_transform + ImageTransformMulti(aug=False) for the test-time branch
+ * (code/datasets/pipelines/transform.py:275-341, 346-378, 149-163): raw uint8 [n_img][H][W][3] (RGB, as the agent holds it:
+ * thinktwice_agent.py:297-300) -> grid_sample(map_grid, bilinear, zeros, align_corners=False) -> T.Resize((newH, newW)) [bilinear,
+ * no antialias: torchvision 0.13.1 of docs/INSTALL.md] -> crop -> /div -> (x - mean) / std.
+ * map_grid: fp32 [H][W][2] normalised (x, y) exactly as transform.py:237-240 builds it (one map for every image; may be NULL without
+ * undistort).  out_nchw: fp32 [n_img][3][outH][outW] (the `img` tensor of the batch dict) and / or out_split8: the row-packed stem's
+ * operand planes [2][n_img][pad_H][pad_W][8 halves] (plane stride split_plane halves; border never written).  Either may be NULL. */
+int tt_preprocess_u8(const tt_preproc_desc* d, const uint8_t* raw, const float* map_grid, float* out_nchw, void* out_split8,
+                     long long split_plane, tt_stream_t stream);
+/* thinktwice_agent.py:340-352: out [n_prev + n_now][4] = [rel_mat (4x4 fp64, row-major, DEVICE) applied to prev's xyz | now], z += z_add (2.5);
+ * float64 arithmetic like the numpy original, intensity untouched. */
+int tt_lidar_stitch(const float* prev, int n_prev, const float* now, int n_now, const double* rel_mat, double z_add, float* out,
+                    tt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (9) training-side ops: what open_loop_training/train.py needs from the op library besides the forward.
+ */
+/* Replaces the indexing backward of ops/voxel_pooling/voxel_pooling.py:57-69: grad_input [B][P][C] (fully written) =
+ * grad_output[pos_memo b][:][pos_memo y][pos_memo x] where pos_memo [B][P][3] != -1, else 0.  grad_output is the (B, C, Y, X)
+ * tensor autograd hands over, addressed by ELEMENT strides (either memory order, no copy). */
+int tt_voxel_pooling_backward(int batch_size, int num_points, int num_channels, const float* grad_output, long long stride_b,
+                              long long stride_c, long long stride_y, long long stride_x, const int* pos_memo, float* grad_input,
+                              tt_stream_t stream);
+/* Replace mmcv's ext_module.ms_deform_attn_forward / ms_deform_attn_backward as the reference calls them
+ * (code/model_code/dense_heads/multi_scale_deformable_attn_function.py:141-147, 172-183; im2col_step has no meaning here).
+ * d: BN = bs, rows_cap = num_queries, heads, levels (<= 4), points, dh, lvl_h / lvl_w / lvl_start = value_spatial_shapes /
+ * value_level_start_index, num_keys; value_ld / value_coff as in tt_msda_forward (0 = dense).
+ * value [bs][num_keys][heads][dh]; sampling_loc [bs][q][heads][levels][points][2] (x, y) in [0, 1]; attn_weight [bs][q][heads][levels][points];
+ * output / grad_output [bs][q][heads*dh].  Backward: grad_value [bs][num_keys][heads][dh] must be ZERO-filled by the caller (as the
+ * reference does: msda:168) and is accumulated with fp32 atomics; grad_sampling_loc / grad_attn_weight are fully written. */
+int tt_ms_deform_attn_forward(const tt_msda_desc* d, const float* value, const float* sampling_loc, const float* attn_weight, float* output,
+                              tt_stream_t stream);
+int tt_ms_deform_attn_backward(const tt_msda_desc* d, const float* value, const float* sampling_loc, const float* attn_weight,
+                               const float* grad_output, float* grad_value, float* grad_sampling_loc, float* grad_attn_weight,
+                               tt_stream_t stream);
+
 #ifdef __cplusplus
 }
 /* C++ linkage, mangled exactly like the reference's own definition (ops/voxel_pooling/src/voxel_pooling_forward_cuda.cu:38,

@@ -93,7 +93,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     from thinktwice_b200 import lib
     pairs = {'tt_conv_desc': lib.ConvDesc, 'tt_lift_splat_desc': lib.LiftSplatDesc, 'tt_voxelize_desc': lib.VoxelizeDesc,
              'tt_rulebook_desc': lib.RulebookDesc, 'tt_sparse_conv_desc': lib.SparseConvDesc, 'tt_look_desc': lib.LookDesc,
-             'tt_msda_desc': lib.MsdaDesc}
+             'tt_msda_desc': lib.MsdaDesc, 'tt_preproc_desc': lib.PreprocDesc}
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "tt_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():

@@ -154,7 +154,7 @@ class EncoderDecoder(nn.Module):
         computed here and uploaded into static device buffers, so the device half is a fixed launch sequence.  The images —
         the bulk of the input bytes — are staged separately (_stage_sweep), sweep by sweep."""
         e = self.eng
-        img = batch['img']
+        img = self._batch_images(batch)
         if img.dim() == 5:
             img = img.unsqueeze(1)
         B, T, N = img.shape[:3]
@@ -178,11 +178,28 @@ class EncoderDecoder(nn.Module):
         e.cur['in.points'] = pb
         lidar2img, ida = self.img_encoder.stage(batch['img_metas'], B, T, N)
         self.decoder.stage(lidar2img, ida)
-        self._imgs = [e.buf(f'in.img.{t}', (B,) + tuple(img.shape[2:])) for t in range(T)]
-        return img, (B, T, N, tuple(img.shape), cap)
+        if img.dtype == torch.uint8:                                # raw camera frames: pre-processed on the device (attach_preprocessor)
+            if self.img_encoder.pre is None:
+                raise lib.TTError("batch['img_raw'] needs model.attach_preprocessor(AgentPreprocessor(...))")
+            self._imgs = [e.buf(f'in.raw.{t}', (B,) + tuple(img.shape[2:]), torch.uint8) for t in range(T)]
+        else:
+            self._imgs = [e.buf(f'in.img.{t}', (B,) + tuple(img.shape[2:])) for t in range(T)]
+        return img, (B, T, N, tuple(img.shape), str(img.dtype), cap)
+
+    @staticmethod
+    def _batch_images(batch):
+        """`img`: (B, T, N, 3, H, W) normalised floats, the reference contract — or `img_raw`: (B, T, N, h, w, 3) uint8 camera frames
+        when the agent-side pre-processing runs on the device."""
+        return batch['img'] if 'img' in batch else batch['img_raw']
+
+    def attach_preprocessor(self, pre):
+        """pre: thinktwice_b200.preprocess.AgentPreprocessor — enables `img_raw` batches (uint8 frames, undistort / resize / crop /
+        normalise fused into the stem's input staging)."""
+        self.img_encoder.pre = pre
+        return self
 
     def _stage_sweep(self, img, t):
-        """images of sweep t of `img` (B, T, N, 3, H, W; host or device, any float / integer dtype) into the sweep's static
+        """images of sweep t of `img` (B, T, N, 3, H, W floats — or (B, T, N, h, w, 3) uint8 raw frames; host or device) into the sweep's static
         device buffer, on the current stream.  Host tensors travel frame by frame: each (N, 3, H, W) block is contiguous, so a
         pinned source goes out as plain asynchronous copies (a strided (B, ...) slice would be gathered on the CPU first)."""
         dst = self._imgs[t]
@@ -341,10 +358,11 @@ class EncoderDecoder(nn.Module):
     @torch.no_grad()
     def forward_inference(self, batch):
         if self.eng is None:
-            self.prepare(batch['img'].device if batch['img'].is_cuda else 'cuda:0')
+            im0 = self._batch_images(batch)
+            self.prepare(im0.device if im0.is_cuda else 'cuda:0')
         self.epoch = 10000
         e = self.eng
-        B_now = batch['img'].shape[0]
+        B_now = self._batch_images(batch).shape[0]
         if getattr(self, '_arena_B', B_now) != B_now:
             self.release_buffers()                                 # one arena at a time: another batch size starts from scratch
         self._arena_B = B_now
@@ -415,7 +433,7 @@ class EncoderDecoder(nn.Module):
         if return_loss:
             raise NotImplementedError('losses / teacher forcing belong to the training path (SURVEY.md §8f f4)')
         pred = self.forward_inference(kwargs)
-        return dict(loss=None, log_vars={}, num_samples=kwargs['img'].shape[0], pred=pred)
+        return dict(loss=None, log_vars={}, num_samples=self._batch_images(kwargs).shape[0], pred=pred)
 
     def forward_test(self, **kwargs):
         """mmdet-style test entry: the batch as keywords -> pred dict."""

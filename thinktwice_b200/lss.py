@@ -242,11 +242,16 @@ class LSS(nn.Module):
         """lss.py:542-621 for one sweep; imgs (B, N, 3, H, W) NCHW on the device; s = sweep distance from the key frame."""
         e, w = self.eng, self.w
         B, N = imgs.shape[:2]
+        raw = imgs.dtype == torch.uint8                              # (B, N, h, w, 3) camera frames: pre-processing fused into the staging
+        if raw and self.pre is None:
+            raise lib.TTError('raw uint8 frames need an AgentPreprocessor (EncoderDecoder.attach_preprocessor)')
         # stem (ResNet conv1 7x7 s2 p3 on 3 channels): the image goes channels-last (4 floats / pixel) into a buffer with
         # a physical zero border (3 px top / bottom / left, 5 right), so a tap ROW of 7 px x 4 floats is 28 contiguous
         # floats = one 32-float K slab of a 7x1 conv over 32 "channels" (x_ld = 4 < Cin = 32, row pitch x_hstride)
         im = imgs.reshape(B * N, *imgs.shape[2:])                      # (a view: every sweep is its own contiguous buffer)
-        H0, W0 = im.shape[2:]
+        H0, W0 = self.final_dim if raw else im.shape[2:]
+        if raw and not e.split:                                      # fp32 engines: the pre-processor writes the NCHW tensor they stage themselves
+            im = self.pre.images(im, out=e.buf('img.f32', (B * N, 3, H0, W0)))
         Wp = W0 + 8
         if e.split:
             # scaled-split engine: 8 halves per pixel (3 channels + 5 zeros; TMA strides are multiples of 16 bytes), so a tap row
@@ -254,7 +259,10 @@ class LSS(nn.Module):
             # (zeroed once at allocation) is never touched
             rows = B * N * (H0 + 6) * Wp
             pbs = e.buf('img.nhwc#s8', (2, rows * 8), torch.float16, zero=True)
-            lib.call('tt_image_to_split8', _p(im.contiguous()), _p(pbs), C.c_longlong(rows * 8), B * N, im.shape[1], H0, W0, H0 + 6, Wp, 3, 3)
+            if raw:                                                  # uint8 frame -> undistort / resize / crop / normalise -> planes, one kernel
+                self.pre.images_to_stem(im, pbs, rows * 8, (H0 + 6, Wp, 3, 3))
+            else:
+                lib.call('tt_image_to_split8', _p(im.contiguous()), _p(pbs), C.c_longlong(rows * 8), B * N, im.shape[1], H0, W0, H0 + 6, Wp, 3, 3)
             x = e.conv(FMap(None, B * N, H0 + 6, W0, 64, ld=8, s=pbs), w['stem'], name='rs.stem', stride=2, act=ACT_RELU,
                        x_hstride=Wp * 8, x_nstride=(H0 + 6) * Wp * 8, fmt='f')    # only the max-pool (an fp32 kernel) reads it
         else:
@@ -311,6 +319,7 @@ class LSS(nn.Module):
     # sweep (half of the camera branch).  The caller vouches for the stream being consecutive (reset_stream() at an episode start).
     stream_cache = False
     _cache_B = None
+    pre = None                     # thinktwice_b200.preprocess.AgentPreprocessor for uint8 `img_raw` batches
 
     def cache_ready(self, B):
         return bool(self.stream_cache and self.queue_len == 2 and self._cache_B == B)

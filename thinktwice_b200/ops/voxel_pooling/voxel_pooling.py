@@ -5,6 +5,8 @@ open_loop_training/ops/voxel_pooling/voxel_pooling.py:10-72: int32 contiguous ge
 features, gradient only w.r.t. the features through the recorded `pos_memo`.  The forward goes through the C ABI
 (`tt_voxel_pooling_forward`, include/tt_b200.h) instead of the pybind module `voxel_pooling_ext`.
 """
+import ctypes as C
+
 import torch
 from torch.autograd import Function
 
@@ -42,11 +44,16 @@ class VoxelPooling(Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        # voxel_pooling.py:57-69 (boolean-mask indexing on the host side of torch) as one gather kernel over the recorded positions
         (memo,) = ctx.saved_tensors
-        kept = (memo != -1)[..., 0]
-        g = grad_out.new_zeros(memo.shape[0], memo.shape[1], grad_out.shape[1])
-        mk = memo[kept]
-        g[kept] = grad_out[mk[..., 0].long(), :, mk[..., 1].long(), mk[..., 2].long()]
+        if not grad_out.is_cuda or grad_out.dtype != torch.float32:
+            raise lib.TTError('voxel_pooling backward needs an fp32 CUDA gradient (no CPU fallback)')
+        B, P = memo.shape[:2]
+        Cc = grad_out.shape[1]
+        g = grad_out.new_empty(B, P, Cc)
+        sb, sc, sy, sx = grad_out.stride()
+        lib.call('tt_voxel_pooling_backward', B, P, Cc, _p(grad_out), C.c_longlong(sb), C.c_longlong(sc), C.c_longlong(sy), C.c_longlong(sx),
+                 _p(memo), _p(g))
         return None, g.reshape(ctx.in_shape), None
 
 
