@@ -67,6 +67,18 @@ def test_ms_deform_attn_forward_and_backward_match_autograd_of_the_oracle(heads,
     out.backward(gout.cuda())
     assert rel(vc.grad, v64.grad) < 1e-5
     assert rel(ac.grad, a64.grad) < 1e-5
-    assert rel(lc.grad, l64.grad) < 1e-4                               # differences of neighbouring values scaled by the map size
-    # the model's fused forward (tt_msda_forward: softmax + offsets inside) and the generic forward agree on the same samples
-    assert float(lc.grad.abs().max()) > 0
+    # the sampled value is piecewise bilinear in the location: its derivative jumps where a pixel coordinate crosses an integer, and a
+    # float32 coordinate within rounding of an integer falls on the other side than the float64 reference (seen: 18.999999 vs 19.0).
+    # Those samples are compared through float32 autograd of the oracle (same side of the jump), all the others against float64.
+    near = torch.zeros(loc.shape[:-1], dtype=torch.bool)
+    for l, (h, w) in enumerate(shapes):
+        for axis, size in ((0, w), (1, h)):
+            pix = loc[:, :, :, l, :, axis].double() * size - 0.5
+            near[:, :, :, l] |= (pix - pix.round()).abs() < 1e-4
+    v32, l32, a32 = (t.clone().requires_grad_(True) for t in (value, loc, aw))
+    msda_pytorch(v32, shapes, l32, a32).backward(gout)
+    far = (~near)[..., None].expand_as(loc)
+    scale = float(l64.grad.abs().max())
+    assert float((lc.grad.cpu().double() - l64.grad)[far].abs().max()) < 1e-4 * scale     # differences of neighbouring values scaled by the map size
+    assert float((lc.grad.cpu() - l32.grad)[~far].abs().max() if (~far).any() else 0.0) < 1e-3 * scale
+    assert float(lc.grad.abs().max()) > 0 and int(near.sum()) < near.numel() // 100

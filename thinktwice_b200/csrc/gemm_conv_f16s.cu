@@ -126,12 +126,13 @@ struct HArgs {
   int cap_rows;
   int tps;               // output-stationary: taps per 64-half K slab (2 when Cin == 32, else 1)
   int splits, k_per;     // split-K: K stages per split
+  int corr_once;         // correction accumulator kept in TMEM for the whole K walk of a work item and drained once (see the MMA issuer)
 };
 
 // GM (gather mode): 0 = dense convolution (TMA box loads); 1 = tap-major sparse convolution (work item = one tap's pair tile,
 // red.add epilogue); 2 = output-stationary sparse convolution (work item = an output-row tile, K runs over ALL taps through the
 // neighbour table, plain fused epilogue — no atomics, no init / finish passes; pays for empty (row, tap) slots with zero rows).
-template <int BN, int STAGES, int GM, bool PAIR, int EW>
+template <int BN, int STAGES, int GM, bool PAIR, int EW, bool CO>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -155,7 +156,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty = bars + STAGES;                        // [STAGES]  MMA -> producer
   uint64_t* acc_full = bars + 2 * STAGES;                 // [2]       MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;            // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* corr_empty = bars + 2 * STAGES + 4;           // [2]       epilogue -> MMA (corr_once: correction buffer of work item t & 1 drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   int* sp_first = reinterpret_cast<int*>(tmem_slot + 2);
   int* sp_cnt = sp_first + MAX_KVOL + 1;
 
@@ -174,7 +176,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); mbar_init(&corr_empty[b], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (GM == 1 && threadIdx.x == 64) {
@@ -361,12 +363,23 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, BN);
       constexpr uint32_t idesc2 = make_idesc_f16(BM, 2 * BN);
-      int ig = 0, cg = 0;
-      for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+      int ig = 0, cg = 0, tg = 0;
+      // corr_once: the correction products (hi x lo' + lo' x hi, weighted 2^-11 in the result) tolerate the truncating accumulation
+      // of the tensor core over the WHOLE K walk — their rounding error is 2^-11 times smaller than the main product's — so only
+      // the main accumulator is folded into fp32 registers every `chunk` stages; the correction accumulator of work item t lives in
+      // buffer t & 1 until the item's last chunk.  Halves the TMEM read traffic of the drains (TMEM reads are 64 B / clk / SM:
+      // 128 KB per K = 128 chunk was 2048 clk against 1536 clk of MMA) at the price of a third N = BN instruction per K step.
+      for (int pt = pair0; pt < total_pairs; pt += pair_step, ++tg) {
         int nt, mt, tap0, count, kb, ke;
         decode(pt, nt, mt, tap0, count, kb, ke);
         int it = kb;
         const int nch = (ke - kb + p.chunk - 1) / p.chunk;
+        const uint32_t t_corr1 = tmem_base + (uint32_t)((tg & 1) * ACC_COLS + BN);
+        if constexpr (CO) {
+          mbar_wait(&corr_empty[tg & 1], ((tg >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+        }
+        bool first_of_item = true;
         for (int c = 0; c < nch; ++c, ++cg) {
           const int b = cg & 1;
           mbar_wait(&acc_empty[b], ((cg >> 1) & 1) ^ 1);
@@ -379,16 +392,23 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(&full[s], (ig / STAGES) & 1);
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-            const uint32_t b_hi = a_hi + 2 * A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
             for (int kk = 0; kk < KE / 16; ++kk) {           // UMMA K = 16 halves = 32 bytes inside the 128-byte swizzle row
               if (p.dbg & 4) break;
               const uint32_t off = kk * 32;
               const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-              umma_f16(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc2, acc);   // hi*hi | hi*lo'
-              umma_f16(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);      // lo'*hi
+              if constexpr (CO) {
+                umma_f16(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);                           // hi*hi
+                umma_f16(t_corr1, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, (first_of_item && kk == 0) ? 0u : 1u);   // hi*lo'
+                umma_f16(t_corr1, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);                            // lo'*hi
+              } else {
+                umma_f16(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc2, acc);   // hi*hi | hi*lo'
+                umma_f16(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);      // lo'*hi
+              }
             }
             first = false;
+            first_of_item = false;
             if (PAIR) tcgen05_commit_mc(&empty[s], 3); else tcgen05_commit(&empty[s]);
           }
           tcgen05_commit(&acc_full[b]);
@@ -405,8 +425,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int HWo = d.OH * d.OW;
     float* tile = tile_all + (warp - 2) * RPP * PITCH;
     bool sat = false;
-    int cg = 0;
-    for (int pt = pair0; pt < total_pairs; pt += pair_step) {
+    int cg = 0, tg = 0;
+    for (int pt = pair0; pt < total_pairs; pt += pair_step, ++tg) {
       int nt, mt, tap, count, kb, ke;
       decode(pt, nt, mt, tap, count, kb, ke);
       const int nch = (ke - kb + p.chunk - 1) / p.chunk;
@@ -492,7 +512,25 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&acc_full[b], (cg >> 1) & 1);
         tcgen05_fence_after();
         const uint32_t t_main = tmem_base + lane_addr + (uint32_t)(b * ACC_COLS + half * HN);
-        if constexpr (EW == 16) {                              // register budget of the 576-thread variant: 16 columns at a time
+        if constexpr (CO) {                                    // main accumulator only: the correction stays in TMEM until the last chunk
+          if constexpr (EW == 16) {
+#pragma unroll
+            for (int c0 = 0; c0 < HN; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(t_main + c0, v);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+            }
+          } else {
+#pragma unroll
+            for (int c0 = 0; c0 < HN; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(t_main + c0, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);                          // fp32 RN
+            }
+          }
+        } else if constexpr (EW == 16) {                       // register budget of the 576-thread variant: 16 columns at a time
 #pragma unroll
           for (int c0 = 0; c0 < HN; c0 += 16) {
             uint32_t v[16], u[16];
@@ -514,6 +552,30 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
+      }
+      if constexpr (CO) {
+        // every MMA of this work item is complete (the last chunk's commit covered them): fold the correction accumulator in, once
+        const uint32_t t_corr = tmem_base + lane_addr + (uint32_t)((tg & 1) * ACC_COLS + BN + half * HN);
+        if constexpr (EW == 16) {
+#pragma unroll
+          for (int c0 = 0; c0 < HN; c0 += 16) {
+            uint32_t u[16];
+            tmem_ld16(t_corr + c0, u);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[c0 + j] = fmaf(__uint_as_float(u[j]), LO_INV, sum[c0 + j]);
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < HN; c0 += 32) {
+            uint32_t u[32];
+            tmem_ld32(t_corr + c0, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] = fmaf(__uint_as_float(u[j]), LO_INV, sum[c0 + j]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&corr_empty[tg & 1])) : "memory");
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       const int sub = lane >> 2, cl = (lane & 3) * 4;
@@ -859,14 +921,18 @@ int num_sms_cached() {
 }
 constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;
 
-template <int BN, int STAGES, int GATHER, bool PAIR, int EW = 8>
-cudaError_t launch_f16s_v(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
+template <int BN, int STAGES, int GATHER, bool PAIR, int EW, bool CO>
+cudaError_t launch_f16s_co(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
   constexpr int smem = STAGES * (2 * BM * KE * 2 + 2 * BN * KE * 2) + 1024 + EPI_BYTES;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
   cfg.dynamicSmemBytes = smem;
   cfg.blockDim = dim3(64 + 32 * EW);
-  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW>, ma, mb, a);
+  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW, CO>, ma, mb, a);
+}
+template <int BN, int STAGES, int GATHER, bool PAIR, int EW = 8>
+cudaError_t launch_f16s_v(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
+  return a.corr_once ? launch_f16s_co<BN, STAGES, GATHER, PAIR, EW, true>(cfg, ma, mb, a) : launch_f16s_co<BN, STAGES, GATHER, PAIR, EW, false>(cfg, ma, mb, a);
 }
 // work items / grid for `tiles` M tiles; debug bit 0x100000 selects the unpaired variant
 template <int BN, int STAGES, int GATHER>
@@ -1040,7 +1106,8 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
   a.res_s = static_cast<const __half*>(io->res_split); a.res_plane = io->res_plane;
   a.res2_s = static_cast<const __half*>(io->res2_split); a.res2_plane = io->res2_plane;
   a.ys = static_cast<__half*>(y_split); a.ys_plane = y_plane;
-  a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;   // 2 stages = K 128 = 8 truncating accumulations per chunk
+  a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;
+  a.corr_once = (g_tt_debug & 0x800000) ? 1 : 0;   // 2 stages = K 128 = 8 truncating accumulations per chunk
   a.n_slabs = (d->Cin + KE - 1) / KE;
   if ((long long)d->N * d->OH * d->OW >= (1ll << 31) - BM || npix_in >= (1ll << 31) - BM) {
     tt_set_error("tt_conv2d_f16s: more than 2^31 pixels");
@@ -1156,6 +1223,7 @@ int tt_sparse_conv_f16s(const tt_sparse_conv_desc* d, const void* feats_in_split
   a.d.act = TT_ACT_NONE;
   a.y = feats_out;
   a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;
+  a.corr_once = (g_tt_debug & 0x800000) ? 1 : 0;
   a.n_slabs = (d->Cin + KE - 1) / KE;
   a.dbg = g_tt_debug & 0xFF;
   a.gx = static_cast<const __half*>(feats_in_split); a.gx_plane = in_plane; a.gx_ld = d->in_ld;
@@ -1211,6 +1279,7 @@ int tt_sparse_conv_os_f16s(const tt_sparse_conv_desc* d, const tt_f16s_io* io, c
   a.res_s = static_cast<const __half*>(io->res_split); a.res_plane = io->res_plane;
   a.y = io->y; a.ys = static_cast<__half*>(io->y_split); a.ys_plane = io->y_plane;
   a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;
+  a.corr_once = (g_tt_debug & 0x800000) ? 1 : 0;
   a.n_slabs = (d->Cin + KE - 1) / KE;
   a.dbg = g_tt_debug & 0xFF;
   a.gx = static_cast<const __half*>(io->x_split); a.gx_plane = io->x_plane; a.gx_ld = d->in_ld;

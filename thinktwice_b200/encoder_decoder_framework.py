@@ -217,17 +217,19 @@ class EncoderDecoder(nn.Module):
     def _phase_history(self, warm=False):
         self.img_encoder.history_device(self._imgs, warm)          # needs the history sweeps' images (none when `warm`)
 
-    def _phase_key(self, lidar, join=None):
-        """key-frame sweep + extract_sensor_feat's tail (framework:238-250) + get_fusion_feat + decoder.  join(): called right
-        before the first kernel that reads the LiDAR branch's output."""
+    def _phase_key(self):
+        """key-frame sweep + the measurement encoder (framework:238-250, 203-204): everything that does not need the LiDAR branch."""
         e = self.eng
         cam = self.img_encoder.key_device(self._imgs)
         cam['bev'] = e.anti_transpose(cam['bev'], 'cam.bev.at')     # rot90(flip): match the Roach BEV
         st = e.static('in.state')
         m = e.linear(e.wrap(st.view(-1, 1, 1, 12)), self.w['meas0'], name='meas.h', act=ACT_RELU)
         meas = e.linear(m, self.w['meas2'], name='meas', act=ACT_RELU)
-        if join is not None:
-            join()
+        return cam, meas
+
+    def _phase_tail(self, cam, meas, lidar):
+        """get_fusion_feat + decoder: where the camera and the LiDAR branch meet."""
+        e = self.eng
         e.mark('camera_encoder')
         flat, bev32, mid, lidar_hi = self.get_fusion_feat(cam['bev'], lidar[0])
         e.mark('bev_fusion')
@@ -246,16 +248,20 @@ class EncoderDecoder(nn.Module):
             lidar = self._phase_lidar()
         e.mark('lidar_encoder')
         self._phase_history(warm)
-        return self._phase_key(lidar, side.join)
+        cam, meas = self._phase_key()
+        side.join()
+        return self._phase_tail(cam, meas, lidar)
 
     # ------------------------------------------------------------------ pipelined forward (host inputs)
     # The batch arrives in HOST memory (thinktwice_agent.py:452-454 moves it tensor by tensor; bench.py's e2e leg hands over pinned
     # tensors): 39 MB of images per frame, 1.26 GB at B = 32 — serial with the forward that is 6 % of the step.  The phases above
     # need their inputs at different times, so the uploads are ordered by first use and overlapped with the kernels:
-    #   main stream : state / matrices / points | history images | history sweeps ............ | key sweep + fusion + decoder
-    #   side stream :                            | LiDAR encoder (starts under the image upload) ...........|
+    #   main stream : state / matrices / points | history images | history sweeps ....... | key sweep ....... | fusion + decoder
+    #   side stream :                            | LiDAR encoder (starts under the image upload) ............|
     #   copy stream :                                             | key-frame images (under the history sweeps) |
-    # The three kernel groups are three CUDA graphs when graph replay is on (a graph cannot wait for an outside event mid-way).
+    # The four kernel groups are four CUDA graphs when graph replay is on (a graph cannot wait for an outside event mid-way); the
+    # LiDAR branch is joined as late as in the one-stream form — its many small kernels only find room between the persistent
+    # convolution kernels, so it needs both sweeps' worth of kernel boundaries to finish unnoticed.
     def _pipelined_forward(self, img, key):
         e = self.eng
         T = img.shape[1]
@@ -265,7 +271,7 @@ class EncoderDecoder(nn.Module):
         if e._copy is None:
             e._copy = torch.cuda.Stream(device=e.device)
         side, copy = e._side, e._copy
-        graphs = self._graphs.get(('pipe',) + key) if getattr(self, 'use_graph', False) else None
+        graphs = self._graphs.get(('pipe',) + key) if getattr(self, 'use_graph', False) else None      # None: launch the kernels eagerly
 
         def run(name, fn):
             if graphs is None:
@@ -295,8 +301,9 @@ class EncoderDecoder(nn.Module):
             ev_key.record(copy)
         run('history', self._phase_history)
         main.wait_event(ev_key)
+        cam, meas = run('key', self._phase_key)
         main.wait_event(ev_lidar)
-        pred = run('key', lambda: self._phase_key(lidar))
+        pred = run('tail', lambda: self._phase_tail(cam, meas, lidar))
         # the next forward's uploads (issued on `main` / `copy`) must not overtake this forward's readers of the input buffers
         ev_done = torch.cuda.Event()
         ev_done.record(main)
@@ -305,20 +312,25 @@ class EncoderDecoder(nn.Module):
         return pred.fresh() if graphs is not None else pred
 
     def _capture_pipeline(self, key):
-        """three graphs over the arena the eager pass just allocated; captured in program order (the key phase holds the LiDAR
-        phase's output maps), replayed by _pipelined_forward on their own streams."""
-        e, graphs, lidar = self.eng, {}, None
-        for name, lane in (('lidar', 1), ('history', 0), ('key', 0)):
+        """four graphs over the arena the eager pass just allocated; captured in program order (the tail holds the output maps of
+        the LiDAR and key phases), replayed by _pipelined_forward on their own streams."""
+        e, graphs, outs = self.eng, {}, {}
+        for name, lane in (('lidar', 1), ('history', 0), ('key', 0), ('tail', 0)):
             g = torch.cuda.CUDAGraph()
             e.lane = lane
             try:
                 with torch.cuda.graph(g):
-                    out = (self._phase_lidar() if name == 'lidar' else self._phase_history() if name == 'history'
-                           else self._phase_key(lidar))
+                    if name == 'lidar':
+                        out = self._phase_lidar()
+                    elif name == 'history':
+                        out = self._phase_history()
+                    elif name == 'key':
+                        out = self._phase_key()
+                    else:
+                        out = self._phase_tail(*outs['key'], outs['lidar'])
             finally:
                 e.lane = 0
-            if name == 'lidar':
-                lidar = out
+            outs[name] = out
             graphs[name] = (g, out)
         self._graphs[('pipe',) + key] = graphs
 
@@ -374,12 +386,17 @@ class EncoderDecoder(nn.Module):
         # host inputs with a history sweep to hide the uploads behind: pipelined (see _pipelined_forward); otherwise one stream
         pipelined = (self.pipeline_uploads and not img.is_cuda and T > 1 and not warm and e.device.type == 'cuda' and e.overlap
                      and e.prof is None and e.marks is None)
+        # Graph mode, first forward of a key: ONE eager pass computes this call's result (and allocates every persistent buffer), then the
+        # graph(s) are captured — capturing executes nothing — and serve the later calls.  (Replaying right after the eager pass would
+        # run the forward twice on one tick: wrong once the forward carries state, i.e. the streaming BEV cache.)
         if pipelined:
-            if use_graph and ('pipe',) + key not in self._graphs:
-                self._pipelined_forward(img, key)                  # eager pass: allocates all persistent buffers
+            fresh_key = use_graph and ('pipe',) + key not in self._graphs
+            if fresh_key:
+                self._graphs[('pipe',) + key] = None               # (eager pass: _pipelined_forward sees no graphs yet)
+            pred = self._own(self._pipelined_forward(img, key))
+            if fresh_key:
                 torch.cuda.synchronize()
                 self._capture_pipeline(key)
-            pred = self._own(self._pipelined_forward(img, key))
         else:
             for t in range(0 if not warm else T - 1, T):
                 self._stage_sweep(img, t)
@@ -388,14 +405,15 @@ class EncoderDecoder(nn.Module):
             else:
                 g = self._graphs.get(key)
                 if g is None:
-                    self._device_forward(warm)                     # eager warm-up: allocates all persistent buffers
+                    pred = self._own(self._device_forward(warm))   # eager: this call's result; allocates all persistent buffers
                     torch.cuda.synchronize()
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
-                        pred = self._device_forward(warm)
-                    g = self._graphs[key] = (graph, pred)
-                g[0].replay()
-                pred = self._own(g[1].fresh())
+                        captured = self._device_forward(warm)
+                    self._graphs[key] = (graph, captured)
+                else:
+                    g[0].replay()
+                    pred = self._own(g[1].fresh())
         if self.img_encoder.stream_cache:
             self.img_encoder._cache_B = B_now
         return pred

@@ -96,6 +96,8 @@ def load():
     for n in ('tt_voxel_pooling_workspace_bytes', 'tt_lift_splat_workspace_bytes', 'tt_voxelize_workspace_bytes',
               'tt_rulebook_workspace_bytes', 'tt_conv2d_workspace_bytes'):
         getattr(lib, n).restype = C.c_size_t
+    if os.environ.get('TT_DEBUG'):                               # kernel-experiment knobs (tt_debug_set) for whole test / bench runs
+        lib.tt_debug_set(int(os.environ['TT_DEBUG'], 0))
     _lib = lib
     return lib
 
