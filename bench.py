@@ -282,6 +282,13 @@ def main():
     launches = launches_per_step * args.steps                    # graph replays execute the same kernel nodes every step
     ms_e2e = timed(host, args.steps, read_back=True)
     stop.set(); th.join(timeout=2)
+    # one traced e2e step: when each phase of the pipelined host-input forward finished, relative to its start (ms)
+    model._pipe_trace = []
+    step(host).cpu()
+    torch.cuda.synchronize()
+    tr = model._pipe_trace
+    model._pipe_trace = None
+    e2e_trace = {lab: round(tr[0][1].elapsed_time(ev), 2) for lab, ev in tr[1:]} if tr else None
 
     # ---- the timed execution mode (graph replay + side stream) must reproduce the plain eager launch sequence
     wp_timed = step(resident).float().cpu().clone()
@@ -364,7 +371,8 @@ def main():
                 e2e={'value': frames / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                      'd2h_bytes_per_step': B * 6 * 4 * 2 * 4, 'ms_per_step': ms_e2e / args.steps,
                      'mode': 'forward_inference(host batch): pinned-host inputs uploaded inside the call, ordered by first use and overlapped with the '
-                             'kernels (LiDAR encoder under the image upload, key-frame images under the history sweeps), waypoints read back every step'},
+                             'kernels (LiDAR encoder under the image upload, key-frame images under the history sweeps), waypoints read back every step',
+                     'phase_done_ms': e2e_trace},
                 roofline={'bound': 'tensor', 'kernel': 'conv_f16s_kernel (implicit-GEMM conv / linear / sparse-conv family on tcgen05, scaled-split fp16 operands; + the few SIMT fallbacks)',
                           'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
                           'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src, 'launches_per_step': n_conv,

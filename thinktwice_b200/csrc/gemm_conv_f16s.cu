@@ -1107,7 +1107,6 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
   a.res2_s = static_cast<const __half*>(io->res2_split); a.res2_plane = io->res2_plane;
   a.ys = static_cast<__half*>(y_split); a.ys_plane = y_plane;
   a.chunk = (g_tt_debug & 0x40000) ? 1 : (g_tt_debug & 0x20000) ? 4 : 2;
-  a.corr_once = (g_tt_debug & 0x800000) ? 1 : 0;   // 2 stages = K 128 = 8 truncating accumulations per chunk
   a.n_slabs = (d->Cin + KE - 1) / KE;
   if ((long long)d->N * d->OH * d->OW >= (1ll << 31) - BM || npix_in >= (1ll << 31) - BM) {
     tt_set_error("tt_conv2d_f16s: more than 2^31 pixels");
@@ -1184,6 +1183,11 @@ int tt_conv2d_f16s(const tt_conv_desc* d, const tt_f16s_io* io, tt_stream_t stre
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // Correction accumulator drained once per work item (corr_once) where the TMEM drains set the pace and the extra N = BN
+  // instruction's operand reads do not: 1x1 layers with 2 .. 4 chunks per tile (K 256 .. 512).  Measured (profiles/r2_summary.md):
+  // 1x1 256->256 @112x224 +23 %; 3x3 256->256 -9 .. -18 % (shared-memory operand reads bound the long-K layers); one-chunk layers
+  // gain nothing.  Debug bits: 0x800000 forces it on everywhere, 0x1000000 off.
+  a.corr_once = (g_tt_debug & 0x1000000) ? 0 : ((g_tt_debug & 0x800000) || (taps == 1 && BN == 128 && a.splits == 1 && k_iters >= 4 && k_iters <= 8)) ? 1 : 0;
   const cudaError_t lerr = BN == 128 ? launch_f16s<128, 3, 0>(cfg, ma, mb, a, a.m_tiles) : launch_f16s<64, 4, 0>(cfg, ma, mb, a, a.m_tiles);
   if (lerr != cudaSuccess) { tt_set_error("tt_conv2d_f16s: cluster launch failed: %s", cudaGetErrorString(lerr)); return TT_ERR_CUDA; }
   ++g_tt_launches;

@@ -279,6 +279,14 @@ class EncoderDecoder(nn.Module):
             graphs[name][0].replay()
             return graphs[name][1]
 
+        trace = self._pipe_trace                                   # bench / diagnosis: a list collects (label, timing event) pairs of one forward
+
+        def tick(label, stream):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                trace.append((label, ev))
+        tick('start', main)
         ev_small = torch.cuda.Event()
         ev_small.record(main)                                      # state, matrices, points are on their way
         side.wait_event(ev_small)
@@ -290,20 +298,26 @@ class EncoderDecoder(nn.Module):
                 e.lane = 0
             ev_lidar = torch.cuda.Event()
             ev_lidar.record(side)
+            tick('lidar_done', side)
         for t in range(T - 1):
             self._stage_sweep(img, t)
         ev_hist = torch.cuda.Event()
         ev_hist.record(main)
+        tick('history_uploaded', main)
         copy.wait_event(ev_hist)                                   # one upload at a time: the history images are needed first
         with torch.cuda.stream(copy):
             self._stage_sweep(img, T - 1)
             ev_key = torch.cuda.Event()
             ev_key.record(copy)
+            tick('key_uploaded', copy)
         run('history', self._phase_history)
+        tick('history_sweeps_done', main)
         main.wait_event(ev_key)
         cam, meas = run('key', self._phase_key)
+        tick('key_sweep_done', main)
         main.wait_event(ev_lidar)
         pred = run('tail', lambda: self._phase_tail(cam, meas, lidar))
+        tick('tail_done', main)
         # the next forward's uploads (issued on `main` / `copy`) must not overtake this forward's readers of the input buffers
         ev_done = torch.cuda.Event()
         ev_done.record(main)
@@ -418,6 +432,7 @@ class EncoderDecoder(nn.Module):
             self.img_encoder._cache_B = B_now
         return pred
 
+    _pipe_trace = None
     pipeline_uploads = True       # overlap the image uploads of a host-resident batch with the kernels (_pipelined_forward)
 
     def enable_streaming_bev_cache(self, flag=True):
