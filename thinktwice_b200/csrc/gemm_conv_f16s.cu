@@ -66,6 +66,50 @@ TT_DEVICE void tma_load_4d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, 
       : "memory");
 }
 
+
+// ---- cta_group::2 (CTA-pair MMA): one instruction of the pair's leader drives both SMs' tensor cores over M = 256 (128 rows from each
+// CTA's own shared memory) and an N whose B rows are split between the two CTAs — each SM reads its A tile and only HALF of B.
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even-ranked CTA (cute: Sm100MmaPeerBitMask)
+TT_DEVICE void umma_f16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// completion of every tcgen05 operation this thread issued so far -> the barrier at this offset in BOTH CTAs of the pair
+TT_DEVICE void tcgen05_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA loads into this CTA's shared memory that signal the LEADER's mbarrier (the pair's MMA issuer waits on one barrier for both CTAs' operands)
+TT_DEVICE void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+TT_DEVICE void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+TT_DEVICE void tma2_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// one arrival on the barrier at this offset in the pair's leader CTA (a plain local arrive when executed by the leader itself)
+TT_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
 // x -> (hi, lo') with saturation to the fp16 range; returns true when x had to be clamped
 TT_DEVICE bool split_h(float x, __half& hi, __half& lo) {
   const float c = fminf(fmaxf(x, -H_MAX), H_MAX);
@@ -132,13 +176,16 @@ struct HArgs {
 // GM (gather mode): 0 = dense convolution (TMA box loads); 1 = tap-major sparse convolution (work item = one tap's pair tile,
 // red.add epilogue); 2 = output-stationary sparse convolution (work item = an output-row tile, K runs over ALL taps through the
 // neighbour table, plain fused epilogue — no atomics, no init / finish passes; pays for empty (row, tap) slots with zero rows).
-template <int BN, int STAGES, int GM, bool PAIR, int EW, bool CO>
+template <int BN, int STAGES, int GM, bool PAIR, int EW, bool CO, int CG>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = BM * KE * 2;                    // 16 KB per plane
   constexpr int B_BYTES = BN * KE * 2;                    // per plane
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  // CG == 2 (cta_group::2): the stage holds this CTA's A planes, ONE 128-row weight block (the hi plane in the leader, the lo' plane in
+  // its peer: together the N = 2 BN operand [B_hi ; B_lo'] of the combined instruction) and this CTA's half of B_hi for the lo' x hi product
+  static_assert(CG == 1 || (PAIR && GM == 0 && !CO), "cta_group::2 path: dense convolutions on CTA pairs only");
+  constexpr int STAGE_BYTES = CG == 2 ? 2 * A_BYTES + B_BYTES + B_BYTES / 2 : 2 * A_BYTES + 2 * B_BYTES;
   constexpr int ACC_COLS = 2 * BN;                        // main | corr
   constexpr int TMEM_COLS = 2 * ACC_COLS;                 // ping-pong
   constexpr int SLAB = 16;
@@ -175,8 +222,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int pair0 = blockIdx.x / CL, pair_step = gridDim.x / CL;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW); mbar_init(&corr_empty[b], EW); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GATHER ? 33 : 1); mbar_init(&empty[s], CG == 2 ? 1 : CL); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CG == 2 ? 2 * EW : EW); mbar_init(&corr_empty[b], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (GM == 1 && threadIdx.x == 64) {
@@ -190,8 +237,13 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     sp_first[p.kvol] = acc;
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (CG == 2) {                                  // the same columns in both CTAs of the pair (issued by both)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -324,7 +376,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===================================================================== TMA producer
     if (lane == 0) {
       const uint32_t a_box = (uint32_t)(p.flat ? BM : p.TH * p.TW) * KE * 2;   // bytes one activation box (one plane) delivers
-      const uint32_t tx = ((p.dbg & 2) ? 0u : 2 * a_box) + 2 * B_BYTES;
+      const uint32_t tx = ((p.dbg & 2) ? 0u : 2 * a_box) + (CG == 2 ? (uint32_t)(B_BYTES + B_BYTES / 2) : 2 * B_BYTES);
       int ig = 0;
       for (int pt = pair0; pt < total_pairs; pt += pair_step) {
         int nt, mt, tap0, count, kb, ke;
@@ -343,6 +395,26 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint8_t* st = smem + s * STAGE_BYTES;
           const int tap = it / p.n_slabs, slab = it - tap * p.n_slabs;
           const int kh = tap / d.KW, kw = tap - kh * d.KW;
+          if constexpr (CG == 2) {
+            // every load of BOTH CTAs completes on the leader's barrier: the leader announces the pair's bytes, the peer only loads
+            // (its complete_tx may land before the announcement: the barrier's pending arrival keeps the phase open)
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * tx);
+            if (!(p.dbg & 2)) {
+              if (p.flat) {
+                tma2_load_3d(st, &map_a, &full[s], slab * KE, cw0, 0);
+                tma2_load_3d(st + A_BYTES, &map_a, &full[s], slab * KE, cw0, 1);
+              } else {
+                const int cw = cw0 + kw * d.dil, ch = ch0 + kh * d.dil;
+                tma2_load_5d(st, &map_a, &full[s], slab * KE, cw, ch, cn, 0);
+                tma2_load_5d(st + A_BYTES, &map_a, &full[s], slab * KE, cw, ch, cn, 1);
+              }
+            }
+            uint8_t* bb = st + 2 * A_BYTES;                           // 128-row block: plane `rank` (hi in the leader, lo' in the peer)
+            tma2_load_4d(bb, &map_b, &full[s], slab * KE, tap, n0, (int)rank);
+            tma2_load_4d(bb + B_BYTES / 2, &map_b, &full[s], slab * KE, tap, n0 + BN / 2, (int)rank);
+            tma2_load_4d(bb + B_BYTES, &map_b, &full[s], slab * KE, tap, n0 + (int)rank * (BN / 2), 0);   // this CTA's half of B_hi
+            continue;
+          }
           mbar_expect_tx(&full[s], tx);
           if (!(p.dbg & 2)) {
             if (p.flat) {
@@ -359,10 +431,10 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
-      constexpr uint32_t idesc2 = make_idesc_f16(BM, 2 * BN);
+    // ===================================================================== MMA issuer (one thread; cta_group::2: of the pair's leader only)
+    if (lane == 0 && (CG == 1 || rank == 0)) {
+      constexpr uint32_t idesc = make_idesc_f16(CG * BM, BN);
+      constexpr uint32_t idesc2 = make_idesc_f16(CG * BM, 2 * BN);
       int ig = 0, cg = 0, tg = 0;
       // corr_once: the correction products (hi x lo' + lo' x hi, weighted 2^-11 in the result) tolerate the truncating accumulation
       // of the tensor core over the WHOLE K walk — their rounding error is 2^-11 times smaller than the main product's — so only
@@ -402,6 +474,10 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 umma_f16(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc, acc);                           // hi*hi
                 umma_f16(t_corr1, make_smem_desc(a_hi + off), make_smem_desc(b_lo + off), idesc, (first_of_item && kk == 0) ? 0u : 1u);   // hi*lo'
                 umma_f16(t_corr1, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);                            // lo'*hi
+              } else if constexpr (CG == 2) {
+                // M = 256 over the pair; B rows split between the CTAs: [B_hi (leader) ; B_lo' (peer)] and the two halves of B_hi
+                umma_f16_2cta(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc2, acc);            // hi*hi | hi*lo'
+                umma_f16_2cta(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + B_BYTES + off), idesc, 1);     // lo'*hi
               } else {
                 umma_f16(t_main, make_smem_desc(a_hi + off), make_smem_desc(b_hi + off), idesc2, acc);   // hi*hi | hi*lo'
                 umma_f16(t_corr, make_smem_desc(a_lo + off), make_smem_desc(b_hi + off), idesc, 1);      // lo'*hi
@@ -409,9 +485,11 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             first = false;
             first_of_item = false;
-            if (PAIR) tcgen05_commit_mc(&empty[s], 3); else tcgen05_commit(&empty[s]);
+            if constexpr (CG == 2) tcgen05_commit_2cta(&empty[s]);
+            else if (PAIR) tcgen05_commit_mc(&empty[s], 3);
+            else tcgen05_commit(&empty[s]);
           }
-          tcgen05_commit(&acc_full[b]);
+          if constexpr (CG == 2) tcgen05_commit_2cta(&acc_full[b]); else tcgen05_commit(&acc_full[b]);
         }
       }
     }
@@ -551,7 +629,10 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_leader(&acc_empty[b]);        // the pair's MMA issuer waits for BOTH CTAs' drains
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[b])) : "memory");
+        }
       }
       if constexpr (CO) {
         // every MMA of this work item is complete (the last chunk's commit covered them): fold the correction accumulator in, once
@@ -660,7 +741,8 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -921,14 +1003,14 @@ int num_sms_cached() {
 }
 constexpr int EPI_BYTES = 8 * 32 * 20 * 4 + BM * (3 * 8 + 4) + 512;
 
-template <int BN, int STAGES, int GATHER, bool PAIR, int EW, bool CO>
+template <int BN, int STAGES, int GATHER, bool PAIR, int EW, bool CO, int CG = 1>
 cudaError_t launch_f16s_co(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
-  constexpr int smem = STAGES * (2 * BM * KE * 2 + 2 * BN * KE * 2) + 1024 + EPI_BYTES;
+  constexpr int smem = STAGES * (2 * BM * KE * 2 + (CG == 2 ? 3 : 4) * BN * KE) + 1024 + EPI_BYTES;
   static bool set = false;
-  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+  if (!set) { cudaFuncSetAttribute(conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW, CO, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
   cfg.dynamicSmemBytes = smem;
   cfg.blockDim = dim3(64 + 32 * EW);
-  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW, CO>, ma, mb, a);
+  return cudaLaunchKernelEx(&cfg, conv_f16s_kernel<BN, STAGES, GATHER, PAIR, EW, CO, CG>, ma, mb, a);
 }
 template <int BN, int STAGES, int GATHER, bool PAIR, int EW = 8>
 cudaError_t launch_f16s_v(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CUtensorMap& mb, const HArgs& a) {
@@ -949,6 +1031,11 @@ cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CU
   // 3x3 trunk layers keep 8 (256->256 @112x224: -6 % with 16).  Debug bit 0x400000 turns the variant off.
   if constexpr (GATHER == 0) {
     if (pair && a.d.KH * a.d.KW == 1 && !(g_tt_debug & 0x400000) && !a.res2 && !a.res2_s) return launch_f16s_v<BN, STAGES, GATHER, true, 16>(cfg, ma, mb, a);
+  }
+  // cta_group::2 (one MMA of the pair's leader over M = 256, each SM reading only half of the weight rows): the long-K dense layers,
+  // whose pace is set by the shared-memory operand reads.  EXPERIMENT behind debug bit 0x2000000 until measured.
+  if constexpr (GATHER == 0 && BN == 128) {
+    if (pair && (g_tt_debug & 0x2000000) && !a.corr_once) return launch_f16s_co<BN, STAGES, GATHER, true, 8, false, 2>(cfg, ma, mb, a);
   }
   return pair ? launch_f16s_v<BN, STAGES, GATHER, true>(cfg, ma, mb, a) : launch_f16s_v<BN, STAGES, GATHER, false>(cfg, ma, mb, a);
 }
