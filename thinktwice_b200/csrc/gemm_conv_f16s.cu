@@ -415,6 +415,10 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tma2_load_4d(bb + B_BYTES, &map_b, &full[s], slab * KE, tap, n0 + (int)rank * (BN / 2), 0);   // this CTA's half of B_hi
             continue;
           }
+          if ((p.dbg & 8) && ig >= STAGES) {                   // diagnosis: no loads after the ring's first fill (stale operands)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+            continue;
+          }
           mbar_expect_tx(&full[s], tx);
           if (!(p.dbg & 2)) {
             if (p.flat) {
@@ -617,7 +621,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 16; ++j) sum[c0 + j] += fmaf(__uint_as_float(u[j]), LO_INV, __uint_as_float(v[j]));
           }
-        } else {
+        } else if (!(p.dbg & 16)) {                            // (knob 16: diagnosis — barriers only, no TMEM reads)
 #pragma unroll
           for (int c0 = 0; c0 < HN; c0 += 32) {
             uint32_t v[32], u[32];
