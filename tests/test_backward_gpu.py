@@ -11,15 +11,15 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize('channels_last_grad', [False, True])
-def test_voxel_pooling_backward_kernel_matches_the_reference_backward(channels_last_grad):
+@pytest.mark.parametrize('channels_last_grad,Cc', [(False, 80), (True, 80), (False, 6), (True, 6)])
+def test_voxel_pooling_backward_kernel_matches_the_reference_backward(channels_last_grad, Cc):
     """ops/voxel_pooling/voxel_pooling.py:57-69: the gradient of a kept point is the output gradient at its recorded (b, y, x); dropped
     points get zero.  Checked against autograd through the oracle's index_add restatement AND the literal indexing of the reference."""
     from oracle.voxel_pool import voxel_pooling_ref
     from thinktwice_b200.ops.voxel_pooling import voxel_pooling
     from thinktwice_b200.ops.voxel_pooling.voxel_pooling import last_pos_memo
     g = torch.Generator().manual_seed(5)
-    B, P, Cc, X, Y, Z = 2, 5000, 80, 21, 21, 1
+    B, P, X, Y, Z = 2, 5000, 21, 21, 1                                    # C = 80: four channels per thread; C = 6: the scalar path
     geom = torch.stack([torch.randint(-3, X + 3, (B, P), generator=g), torch.randint(-3, Y + 3, (B, P), generator=g),
                         torch.randint(-1, Z + 1, (B, P), generator=g)], -1).int()
     feats = torch.randn(B, P, Cc, generator=g)

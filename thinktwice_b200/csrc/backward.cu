@@ -23,6 +23,23 @@ __global__ void voxel_pool_bwd_kernel(const float* __restrict__ grad_out, long l
     grad_in[i] = mb != -1 ? __ldg(grad_out + mb * sb + c * sc + my * sy + mx * sx) : 0.f;
   }
 }
+// C % 4 == 0: one thread = 4 channels of a point — the memo is read once per 16 bytes written, the store is one 128-bit transaction
+// (the op is a pure write stream: B * P * C floats out, the (B, C, Y, X) gradient it gathers from is cache resident)
+__global__ void voxel_pool_bwd4_kernel(const float* __restrict__ grad_out, long long sb, long long sc, long long sy, long long sx,
+                                       const int* __restrict__ pos_memo, float4* __restrict__ grad_in, long long total4, int C4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long bp = i / C4;
+    const int mb = __ldg(pos_memo + bp * 3), my = __ldg(pos_memo + bp * 3 + 1), mx = __ldg(pos_memo + bp * 3 + 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mb != -1) {
+      const float* g = grad_out + mb * sb + c * sc + my * sy + mx * sx;
+      if (sc == 1) v = __ldg(reinterpret_cast<const float4*>(g));     // channels-last gradient (16-byte aligned: checked by the host)
+      else v = make_float4(__ldg(g), __ldg(g + sc), __ldg(g + 2 * sc), __ldg(g + 3 * sc));
+    }
+    grad_in[i] = v;
+  }
+}
 
 struct Tap {
   bool in;            // the sampling point touches the map at all (ms_deform_attn: h_im > -1 && w_im > -1 && h_im < H && w_im < W)
@@ -142,9 +159,17 @@ int tt_voxel_pooling_backward(int batch_size, int num_points, int num_channels, 
              "bad arguments");
   const long long total = (long long)batch_size * num_points * num_channels;
   if (total == 0) return TT_OK;
-  const long long want = (total + 255) / 256;
-  voxel_pool_bwd_kernel<<<(int)(want > 148 * 32 ? 148 * 32 : want), 256, 0, (cudaStream_t)stream>>>(grad_output, stride_b, stride_c, stride_y, stride_x,
-                                                                                                    pos_memo, grad_input, total, num_channels);
+  const bool vec4 = num_channels % 4 == 0 && (reinterpret_cast<uintptr_t>(grad_input) & 15) == 0 &&
+                    (stride_c != 1 || ((reinterpret_cast<uintptr_t>(grad_output) & 15) == 0 && ((stride_b | stride_y | stride_x) & 3) == 0));
+  if (vec4) {
+    const long long total4 = total / 4, want4 = (total4 + 255) / 256;
+    voxel_pool_bwd4_kernel<<<(int)(want4 > 148 * 32 ? 148 * 32 : want4), 256, 0, (cudaStream_t)stream>>>(
+        grad_output, stride_b, stride_c, stride_y, stride_x, pos_memo, reinterpret_cast<float4*>(grad_input), total4, num_channels / 4);
+  } else {
+    const long long want = (total + 255) / 256;
+    voxel_pool_bwd_kernel<<<(int)(want > 148 * 32 ? 148 * 32 : want), 256, 0, (cudaStream_t)stream>>>(grad_output, stride_b, stride_c, stride_y, stride_x,
+                                                                                                      pos_memo, grad_input, total, num_channels);
+  }
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_voxel_pooling_backward");
   return TT_OK;
