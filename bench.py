@@ -284,11 +284,17 @@ def main():
     stop.set(); th.join(timeout=2)
     # one traced e2e step: when each phase of the pipelined host-input forward finished, relative to its start (ms)
     model._pipe_trace = []
+    t_call = time.perf_counter()
     step(host).cpu()
+    t_ret = time.perf_counter()
     torch.cuda.synchronize()
     tr = model._pipe_trace
     model._pipe_trace = None
-    e2e_trace = {lab: round(tr[0][1].elapsed_time(ev), 2) for lab, ev in tr[1:]} if tr else None
+    e2e_trace = None
+    if tr:                                                       # device: when each phase finished; host: when its launch was issued
+        e2e_trace = {lab: round(tr[0][1].elapsed_time(ev), 2) for lab, ev, _ in tr[1:]}
+        e2e_trace['host_issue_ms'] = {lab: round((t - t_call) * 1e3, 2) for lab, _, t in tr}
+        e2e_trace['host_call_to_return_ms'] = round((t_ret - t_call) * 1e3, 2)
 
     # ---- the timed execution mode (graph replay + side stream) must reproduce the plain eager launch sequence
     wp_timed = step(resident).float().cpu().clone()

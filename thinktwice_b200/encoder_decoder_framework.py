@@ -5,6 +5,7 @@ same registry name, same constructor keywords, same `forward_inference(batch)` /
 `control_pid` signatures and the same pred dict, so `leaderboard/team_code/thinktwice_agent.py:456-461`
 calls it unchanged.  The forward runs entirely in libtt_b200 (no eager / CPU fallback).
 """
+import time
 from collections import deque
 
 import numpy as np
@@ -149,10 +150,12 @@ class EncoderDecoder(nn.Module):
         return flat, f21, [None, None, f21] + mids, lidar_feat
 
     # ------------------------------------------------------------------ forward (framework:194-210, 238-250)
-    def stage(self, batch):
+    def stage(self, batch, mats=True):
         """Host half of forward_inference: everything that touches host data (state vector, img_metas matrices) is
         computed here and uploaded into static device buffers, so the device half is a fixed launch sequence.  The images —
-        the bulk of the input bytes — are staged separately (_stage_sweep), sweep by sweep."""
+        the bulk of the input bytes — are staged separately (_stage_sweep), sweep by sweep.  mats=False leaves the img_metas
+        matrices (python loops + 4x4 inverses on the CPU) to a later stage_mats() call: the pipelined forward runs them while the
+        image upload and the LiDAR encoder are already under way."""
         e = self.eng
         img = self._batch_images(batch)
         if img.dim() == 5:
@@ -176,8 +179,8 @@ class EncoderDecoder(nn.Module):
             e.fill(pb, 1e30)
         pb[:, :P].copy_(pts, non_blocking=True)
         e.cur['in.points'] = pb
-        lidar2img, ida = self.img_encoder.stage(batch['img_metas'], B, T, N)
-        self.decoder.stage(lidar2img, ida)
+        if mats:
+            self.stage_mats(batch, B, T, N)
         if img.dtype == torch.uint8:                                # raw camera frames: pre-processed on the device (attach_preprocessor)
             if self.img_encoder.pre is None:
                 raise lib.TTError("batch['img_raw'] needs model.attach_preprocessor(AgentPreprocessor(...))")
@@ -185,6 +188,10 @@ class EncoderDecoder(nn.Module):
         else:
             self._imgs = [e.buf(f'in.img.{t}', (B,) + tuple(img.shape[2:])) for t in range(T)]
         return img, (B, T, N, tuple(img.shape), str(img.dtype), cap)
+
+    def stage_mats(self, batch, B, T, N):
+        lidar2img, ida = self.img_encoder.stage(batch['img_metas'], B, T, N)
+        self.decoder.stage(lidar2img, ida)
 
     @staticmethod
     def _batch_images(batch):
@@ -262,9 +269,9 @@ class EncoderDecoder(nn.Module):
     # The four kernel groups are four CUDA graphs when graph replay is on (a graph cannot wait for an outside event mid-way); the
     # LiDAR branch is joined as late as in the one-stream form — its many small kernels only find room between the persistent
     # convolution kernels, so it needs both sweeps' worth of kernel boundaries to finish unnoticed.
-    def _pipelined_forward(self, img, key):
+    def _pipelined_forward(self, img, key, batch):
         e = self.eng
-        T = img.shape[1]
+        B, T, N = img.shape[:3]
         main = torch.cuda.current_stream()
         if e._side is None:
             e._side = torch.cuda.Stream(device=e.device)
@@ -285,7 +292,7 @@ class EncoderDecoder(nn.Module):
             if trace is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(stream)
-                trace.append((label, ev))
+                trace.append((label, ev, time.perf_counter()))
         tick('start', main)
         ev_small = torch.cuda.Event()
         ev_small.record(main)                                      # state, matrices, points are on their way
@@ -301,6 +308,7 @@ class EncoderDecoder(nn.Module):
             tick('lidar_done', side)
         for t in range(T - 1):
             self._stage_sweep(img, t)
+        self.stage_mats(batch, B, T, N)                            # CPU work + small uploads, under the image DMA and the LiDAR kernels
         ev_hist = torch.cuda.Event()
         ev_hist.record(main)
         tick('history_uploaded', main)
@@ -393,13 +401,14 @@ class EncoderDecoder(nn.Module):
             self.release_buffers()                                 # one arena at a time: another batch size starts from scratch
         self._arena_B = B_now
         warm = self.img_encoder.cache_ready(B_now)                 # streaming BEV cache: the previous tick left its key-frame BEV behind
-        img, key = self.stage(batch)
+        im0 = self._batch_images(batch)
+        # host inputs with a history sweep to hide the uploads behind: pipelined (see _pipelined_forward); otherwise one stream
+        pipelined = (self.pipeline_uploads and not im0.is_cuda and (im0.dim() == 6 and im0.shape[1] > 1) and not warm and e.device.type == 'cuda'
+                     and e.overlap and e.prof is None and e.marks is None)
+        img, key = self.stage(batch, mats=not pipelined)
         key = key + (warm,)
         T = img.shape[1]
         use_graph = getattr(self, 'use_graph', False)
-        # host inputs with a history sweep to hide the uploads behind: pipelined (see _pipelined_forward); otherwise one stream
-        pipelined = (self.pipeline_uploads and not img.is_cuda and T > 1 and not warm and e.device.type == 'cuda' and e.overlap
-                     and e.prof is None and e.marks is None)
         # Graph mode, first forward of a key: ONE eager pass computes this call's result (and allocates every persistent buffer), then the
         # graph(s) are captured — capturing executes nothing — and serve the later calls.  (Replaying right after the eager pass would
         # run the forward twice on one tick: wrong once the forward carries state, i.e. the streaming BEV cache.)
@@ -407,7 +416,7 @@ class EncoderDecoder(nn.Module):
             fresh_key = use_graph and ('pipe',) + key not in self._graphs
             if fresh_key:
                 self._graphs[('pipe',) + key] = None               # (eager pass: _pipelined_forward sees no graphs yet)
-            pred = self._own(self._pipelined_forward(img, key))
+            pred = self._own(self._pipelined_forward(img, key, batch))
             if fresh_key:
                 torch.cuda.synchronize()
                 self._capture_pipeline(key)
