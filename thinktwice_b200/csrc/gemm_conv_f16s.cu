@@ -298,6 +298,7 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int n0 = nt * BN;
       const int* pin = GM == 1 ? p.pairs_in + (long long)tap * p.pair_cap : nullptr;
       int rows[4];
+      int nxa[4] = {-1, -1, -1, -1}, nxb[4] = {-1, -1, -1, -1};   // neighbour indices of the next stage / tap (GM == 2)
       if (GM == 1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -309,13 +310,27 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int s = ig % STAGES;
         if (GM == 2 && p.tps == 2) {
           // ---- two taps per K slab (Cin = 32): chunks 0..3 of a row come from the neighbour under tap 2 it, chunks 4..7 from tap 2 it + 1
+          // (the neighbour indices of stage it + 1 are fetched while stage it's copies are issued: their latency was exposed once per stage)
           int ra[4], rb[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int m = mt * BM + lane + 32 * i;
-            const int* nb = p.nbr + (long long)m * p.kvol + 2 * it;
-            ra[i] = m < count ? __ldg(nb) : -1;
-            rb[i] = (m < count && 2 * it + 1 < p.kvol) ? __ldg(nb + 1) : -1;
+            if (it == kb) {
+              const int m = mt * BM + lane + 32 * i;
+              const int* nb = p.nbr + (long long)m * p.kvol + 2 * it;
+              ra[i] = m < count ? __ldg(nb) : -1;
+              rb[i] = (m < count && 2 * it + 1 < p.kvol) ? __ldg(nb + 1) : -1;
+            } else {
+              ra[i] = nxa[i]; rb[i] = nxb[i];
+            }
+          }
+          if (it + 1 < ke) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = mt * BM + lane + 32 * i;
+              const int* nb = p.nbr + (long long)m * p.kvol + 2 * (it + 1);
+              nxa[i] = m < count ? __ldg(nb) : -1;
+              nxb[i] = (m < count && 2 * (it + 1) + 1 < p.kvol) ? __ldg(nb + 1) : -1;
+            }
           }
           mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
@@ -346,7 +361,15 @@ conv_f16s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int m = mt * BM + lane + 32 * i;
-            rows[i] = m < count ? __ldg(p.nbr + (long long)m * p.kvol + ktap) : -1;       // -1: no input site under this tap
+            if (it == kb) rows[i] = m < count ? __ldg(p.nbr + (long long)m * p.kvol + ktap) : -1;       // -1: no input site under this tap
+            else rows[i] = nxa[i];                                                                       // fetched one tap ahead
+          }
+          if (ktap + 1 < taps) {                              // next tap's neighbours: in flight while this tap's copies are issued
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = mt * BM + lane + 32 * i;
+              nxa[i] = m < count ? __ldg(p.nbr + (long long)m * p.kvol + ktap + 1) : -1;
+            }
           }
         }
         mbar_wait(&empty[s], ((ig / STAGES) & 1) ^ 1);
