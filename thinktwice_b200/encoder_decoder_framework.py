@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import lib
-from .engine import Engine, FMap
+from .engine import Engine
 from .lib import ACT_RELU
 from .params import ParamTree, param_spec
 from .registry import DETECTORS, build_backbone, build_head
