@@ -361,6 +361,9 @@ int tt_preprocess_u8(const tt_preproc_desc* d, const uint8_t* raw, const float* 
  * float64 arithmetic like the numpy original, intensity untouched. */
 int tt_lidar_stitch(const float* prev, int n_prev, const float* now, int n_now, const double* rel_mat, double z_add, float* out,
                     tt_stream_t stream);
+/* code/datasets/carla_dataset.py:314-328 (union2one): dst [n][5] = [curr2key (4x4 fp32, row-major, DEVICE; NULL = key frame: copy) applied to the
+ * (x, y, z, intensity) 4-vector of src [n][4] | timestamp]; the caller places the sweeps back to back (key frame first). */
+int tt_points_union(const float* src, int n, const float* curr2key, float timestamp, float* dst, tt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (9) training-side ops: what open_loop_training/train.py needs from the op library besides the forward.

@@ -8,6 +8,8 @@ What the reference does between the CARLA sensors and `forward_inference`, in pl
 * `image_normalize`      — `ImageTransformMulti.__call__`, `aug=False` (transform.py:161-163): `/255`, `T.Normalize`.
 * `undistort_grid`       — the map of `IDAImageTransform.__init__` (transform.py:233-240) from the rig constants (:47-51).
 * `stitch_lidar`         — the half-sweep stitching of `thinktwice_agent.py:340-352` (numpy float64 like the original).
+* `union2one`            — `carla_dataset.py:250-334`: per-frame metas of a queue (can_bus deltas, `curr2key`, `currlidar2keycam`) and the
+                           multi-sweep point cloud (earlier frames moved into the key frame, timestamp column).
 
 `T.Resize` on a float tensor is `F.interpolate(mode='bilinear', align_corners=False, antialias=...)`; the reference pins
 torchvision 0.13.1 (docs/INSTALL.md:12) whose tensor path does NOT antialias, so `antialias=False` is the reference behaviour
@@ -25,6 +27,11 @@ MTX = np.array([[214.35935394, 0, 800], [0, 214.35935394, 450], [0, 0, 1]])
 DIST = np.array([[0.00888296, -0.00130899, 0.00012061, -0.00338673, 0.00028834]])
 NEWCAMERAMTX = np.array([[304.14395142, 0, 788.25758876], [0, 221.49429321, 449.78972161], [0, 0, 1]])
 MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]          # transform.py:144
+LIDAR2CAM_ALL = np.array([                                          # transform.py:25-30 in camera order front / left / right / back (thinktwice.py:102)
+    [[0.0, 1.0, 0.0, 0.0], [0.0, 0.0, -1.0, 2.5], [1.0, 0.0, 0.0, -1.5], [0.0, 0.0, 0.0, 1.0]],
+    [[1.0, 0.0, 0.0, 0.0], [0.0, 0.0, -1.0, 2.5], [0.0, -1.0, 0.0, -0.3], [0.0, 0.0, 0.0, 1.0]],
+    [[-1.0, 0.0, 0.0, 0.0], [0.0, 0.0, -1.0, 2.5], [0.0, 1.0, 0.0, -0.3], [0.0, 0.0, 0.0, 1.0]],
+    [[0.0, -1.0, 0.0, 0.0], [0.0, 0.0, -1.0, 2.5], [-1.0, 0.0, 0.0, -1.6], [0.0, 0.0, 0.0, 1.0]]])
 
 
 def undistort_grid(size=(1600, 900)):
@@ -94,3 +101,59 @@ def stitch_lidar(prev_lidar, now_lidar, rel_mat, z_add=2.5):
     saved = np.concatenate([moved, now_lidar], axis=0).copy()
     saved[:, 2] += z_add
     return saved.astype(np.float32)
+
+
+def get_ego_shift(delta_x, delta_y, ego_angle):
+    """carla_dataset.py:250-257."""
+    translation_length = np.sqrt(delta_x ** 2 + delta_y ** 2)
+    translation_angle = np.arctan2(delta_y, delta_x) / np.pi * 180
+    bev_angle = ego_angle - translation_angle
+    shift_y = translation_length * np.cos(bev_angle / 180 * np.pi)
+    shift_x = translation_length * np.sin(bev_angle / 180 * np.pi)
+    return shift_x, shift_y
+
+
+def union2one(can_bus_list, lidar2cam, points_list):
+    """carla_dataset.py:261-334 without the image pipeline: can_bus_list — one (18,) float64 array per queue entry (oldest first, key
+    frame last), lidar2cam (N, 4, 4) float32 tensor, points_list — one (n_i, 4) float32 tensor per entry.
+    -> (metas: list of dicts with can_bus / prev_bev / curr2key / currlidar2keycam, points (1, sum n_i, 5))."""
+    import copy
+    n = len(can_bus_list)
+    metas, prev_pos, prev_angle = [], None, None
+    for i in range(n):
+        meta = {'can_bus': copy.deepcopy(can_bus_list[i]), 'lidar2cam': lidar2cam}
+        if i == 0:
+            meta['prev_bev'] = False
+            prev_pos, prev_angle = copy.deepcopy(meta['can_bus'][:3]), copy.deepcopy(meta['can_bus'][-1])
+            meta['can_bus'][:3] = 0
+            meta['can_bus'][-1] = 0
+        else:
+            meta['prev_bev'] = True
+            tmp_pos, tmp_angle = copy.deepcopy(meta['can_bus'][:3]), copy.deepcopy(meta['can_bus'][-1])
+            meta['can_bus'][:3] -= prev_pos
+            meta['can_bus'][-1] -= prev_angle
+            prev_pos, prev_angle = copy.deepcopy(tmp_pos), copy.deepcopy(tmp_angle)
+        metas.append(meta)
+    metas[-1]['curr2key'] = torch.eye(4)
+    metas[-1]['currlidar2keycam'] = metas[-1]['lidar2cam']
+    key_x, key_y = can_bus_list[-1][:2]
+    key_yaw = can_bus_list[-1][-2]
+    for i in range(n - 2, -1, -1):
+        curr_x, curr_y = can_bus_list[i][0], can_bus_list[i][1]
+        c2k_x, c2k_y = get_ego_shift(key_x - curr_x, key_y - curr_y, key_yaw / np.pi * 180)
+        ang = key_yaw - can_bus_list[i][-2]
+        R = torch.eye(4)
+        R[:2, :2] = torch.Tensor([[np.cos(ang), np.sin(ang)], [-np.sin(ang), np.cos(ang)]])
+        T = torch.eye(4)
+        T[0, 3], T[1, 3] = c2k_x, c2k_y
+        metas[i]['curr2key'] = R @ T
+        metas[i]['currlidar2keycam'] = metas[i]['lidar2cam'] @ metas[i]['curr2key']
+    pts = torch.cat([points_list[-1], torch.zeros(points_list[-1].shape[0], 1)], dim=1)
+    pts[:, 4] = 0
+    out = [pts]
+    for i in range(n - 2, -1, -1):
+        sw = torch.cat([copy.deepcopy(points_list[i]), torch.zeros(points_list[i].shape[0], 1)], dim=1)
+        sw[:, :4] = (metas[i]['curr2key'] @ sw[:, :4].T).T        # (x, y, z, intensity) as a homogeneous vector: reference quirk
+        sw[:, 4] = i - (n - 1)
+        out.append(sw)
+    return metas, torch.cat(out).unsqueeze(0)

@@ -125,3 +125,19 @@ def test_kernel_operation_order_equals_torch_bit_for_bit(undistort):
     want = op.image_normalize(want).reshape(6, 3, 44, 88)
     got = kernel_order_restatement(raw.reshape(6, 90, 160, 3), grid, conf, undistort)
     assert torch.equal(got, want), float((got - want).abs().max())
+
+
+def test_union2one_restatements_match_the_reference_function(golden):
+    """carla_dataset.py:250-334 run from its own source text (golden) vs the oracle restatement and vs the product's host half (union_metas)."""
+    from make_preprocess_golden import union_case
+    from oracle import preprocess as op
+    from thinktwice_b200 import preprocess as pp
+    can, pts = union_case()
+    l2c = torch.from_numpy(op.LIDAR2CAM_ALL.astype(np.float32))
+    metas, points = op.union2one(can, l2c, pts)
+    assert np.array_equal(points.numpy(), golden['u_points'])
+    for got in (metas, pp.union_metas(can, l2c)):
+        assert np.array_equal(np.stack([m['curr2key'].numpy() for m in got]), golden['u_curr2key'])
+        assert np.array_equal(np.stack([m['currlidar2keycam'].numpy() for m in got]), golden['u_l2kc'])
+        assert np.array_equal(np.stack([m['can_bus'] for m in got]), golden['u_can_bus'])
+        assert [bool(m['prev_bev']) for m in got] == [bool(v) for v in golden['u_prev_bev']]

@@ -133,3 +133,18 @@ def test_model_fed_with_raw_frames_equals_model_fed_with_the_preprocessed_tensor
                 assert err < 1e-4, (use_graph, i, k, err)
     model.use_graph = False
     assert model.f16s_saturations() == 0
+
+
+def test_union_points_matches_the_reference_union2one():
+    """carla_dataset.py:314-328 on the device against the golden output of the reference's own function."""
+    from make_preprocess_golden import union_case
+    from oracle.preprocess import LIDAR2CAM_ALL
+    from thinktwice_b200.preprocess import AgentPreprocessor, union_metas
+    can, pts = union_case()
+    metas = union_metas(can, torch.from_numpy(LIDAR2CAM_ALL.astype(np.float32)))
+    pre = AgentPreprocessor(dict(undistort=False, num_cams=1), dict(CONF, H=8, W=8, final_dim=(4, 4)), 'cuda:0')
+    got = pre.union_points(pts, metas).cpu().numpy()
+    golden = np.load(os.path.join(HERE, 'golden', 'ref_preprocess.npz'))['u_points']
+    assert got.shape == golden.shape
+    assert np.array_equal(got[..., 4], golden[..., 4]) and np.array_equal(got[0, :pts[1].shape[0], :4], pts[1].numpy())
+    assert float(np.abs(got - golden).max()) <= 1e-5 * float(np.abs(golden).max())     # fp32 4-term dot products: order of summation only

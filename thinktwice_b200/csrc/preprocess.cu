@@ -137,6 +137,21 @@ __global__ void lidar_stitch_kernel(const float* __restrict__ prev, int n_prev, 
   reinterpret_cast<float4*>(out)[i] = o;
 }
 
+// carla_dataset.py:314-328 (union2one, "dense-fusion"): a sweep's (x, y, z, intensity) rows multiplied by curr2key as 4-vectors (the
+// reference uses the intensity as the homogeneous coordinate) plus a timestamp column; mat == NULL: the key frame (copied, timestamp 0)
+__global__ void points_union_kernel(const float* __restrict__ src, int n, const float* __restrict__ mat, float ts, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(src) + i);
+  float o[4] = {p.x, p.y, p.z, p.w};
+  if (mat) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = fmaf(mat[k * 4 + 3], p.w, fmaf(mat[k * 4 + 2], p.z, fmaf(mat[k * 4 + 1], p.y, mat[k * 4] * p.x)));
+  }
+  float* d = dst + (long long)i * 5;
+  d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; d[3] = o[3]; d[4] = ts;
+}
+
 }  // namespace
 
 extern "C" {
@@ -174,6 +189,15 @@ int tt_lidar_stitch(const float* prev, int n_prev, const float* now, int n_now, 
   lidar_stitch_kernel<<<tt_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(prev, n_prev, now, n_now, rel_mat, z_add, out);
   ++g_tt_launches;
   TT_CHECK_LAUNCH("tt_lidar_stitch");
+  return TT_OK;
+}
+
+int tt_points_union(const float* src, int n, const float* curr2key, float timestamp, float* dst, tt_stream_t stream) {
+  TT_REQUIRE(n >= 0 && (n == 0 || (src && dst)) && (reinterpret_cast<uintptr_t>(src) & 15) == 0, "tt_points_union", "bad arguments ([n][4] floats, 16-byte aligned)");
+  if (n == 0) return TT_OK;
+  points_union_kernel<<<tt_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(src, n, curr2key, timestamp, dst);
+  ++g_tt_launches;
+  TT_CHECK_LAUNCH("tt_points_union");
   return TT_OK;
 }
 

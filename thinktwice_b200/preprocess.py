@@ -55,6 +55,44 @@ def obtain_inv_transform_matrix(x, y, yaw):
     return np.array([[cy, sy, 0.0, ox], [-sy, cy, 0.0, oy], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
 
 
+def get_ego_shift(delta_x, delta_y, ego_angle):
+    """code/datasets/carla_dataset.py:250-257."""
+    length = np.sqrt(delta_x ** 2 + delta_y ** 2)
+    bev_angle = ego_angle - np.arctan2(delta_y, delta_x) / np.pi * 180
+    return length * np.sin(bev_angle / 180 * np.pi), length * np.cos(bev_angle / 180 * np.pi)
+
+
+def union_metas(can_bus_list, lidar2cam):
+    """The matrix half of `union2one` (code/datasets/carla_dataset.py:261-312): one meta dict per queue entry (oldest first, key frame last)
+    with the can_bus deltas, `prev_bev`, `curr2key` and `currlidar2keycam` (host: a handful of 4 x 4 products per tick)."""
+    n = len(can_bus_list)
+    metas, prev_pos, prev_angle = [], None, None
+    for i, cb in enumerate(can_bus_list):
+        cb = np.array(cb, dtype=np.float64, copy=True)
+        pos, ang = cb[:3].copy(), float(cb[-1])
+        if i == 0:
+            cb[:3] = 0
+            cb[-1] = 0
+        else:
+            cb[:3] -= prev_pos
+            cb[-1] -= prev_angle
+        prev_pos, prev_angle = pos, ang
+        metas.append({'can_bus': cb, 'prev_bev': i > 0, 'lidar2cam': lidar2cam})
+    metas[-1]['curr2key'] = torch.eye(4)
+    metas[-1]['currlidar2keycam'] = lidar2cam
+    key_x, key_y, key_yaw = can_bus_list[-1][0], can_bus_list[-1][1], can_bus_list[-1][-2]
+    for i in range(n - 2, -1, -1):
+        sx, sy = get_ego_shift(key_x - can_bus_list[i][0], key_y - can_bus_list[i][1], key_yaw / np.pi * 180)
+        ang = key_yaw - can_bus_list[i][-2]
+        R = torch.eye(4)
+        R[:2, :2] = torch.Tensor([[np.cos(ang), np.sin(ang)], [-np.sin(ang), np.cos(ang)]])
+        T = torch.eye(4)
+        T[0, 3], T[1, 3] = sx, sy
+        metas[i]['curr2key'] = R @ T
+        metas[i]['currlidar2keycam'] = lidar2cam @ metas[i]['curr2key']
+    return metas
+
+
 class AgentPreprocessor:
     """GPU stand-in for `IDAImageTransform(cfg, ida_aug_conf, is_train=False)` + `ImageTransformMulti(aug=False)` and the LiDAR
     stitching of the agent's `tick()`.  cfg keys used: 'undistort' (default True), 'num_cams'."""
@@ -122,6 +160,20 @@ class AgentPreprocessor:
         prev = obtain_transform_matrix(pose_prev[1], -pose_prev[0], pose_prev[2] - np.pi / 2)
         now_inv = obtain_inv_transform_matrix(pose_now[1], -pose_now[0], pose_now[2] - np.pi / 2)
         return np.dot(now_inv, prev)
+
+    def union_points(self, points_list, metas):
+        """The point half of `union2one` (carla_dataset.py:314-328): points_list — one (n_i, 4) cloud per queue entry (oldest first, key frame
+        last; host or device), metas from union_metas() -> (1, sum n_i, 5) on the device: key frame first with timestamp 0, then the earlier
+        frames (newest first) moved by their `curr2key`, timestamp i - (T - 1)."""
+        clouds = [torch.as_tensor(p).to(self.device, torch.float32).contiguous() for p in points_list]
+        n = len(clouds)
+        out = torch.empty(1, sum(c.shape[0] for c in clouds), 5, dtype=torch.float32, device=self.device)
+        off = 0
+        for i in [n - 1] + list(range(n - 2, -1, -1)):
+            mat = None if i == n - 1 else metas[i]['curr2key'].to(self.device, torch.float32).contiguous()
+            lib.call('tt_points_union', _p(clouds[i]), clouds[i].shape[0], _p(mat), C.c_float(float(i - (n - 1))), _p(out, off * 5))
+            off += clouds[i].shape[0]
+        return out
 
     def stitch_lidar(self, prev, now, rel_mat, z_add=2.5):
         """prev / now: (n, 4) float32 half sweeps (host or device; prev may be None on the first tick) -> (n_prev + n_now, 4) on the device."""
