@@ -365,15 +365,19 @@ def main():
         lat_stream = e0.elapsed_time(e1) / 20
         model.enable_streaming_bev_cache(False)
         # what the agent sees per tick: the batch in (pinned) host memory, uploads inside the call, waypoints read back (thinktwice_agent.py:452-461)
-        for k in ('img', 'points', 'speed', 'target_point', 'target_command'):
-            host1[k] = host1[k].pin_memory()
-        for _ in range(4):
-            model.forward_inference(host1)['pred_wp'].cpu()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(20):
-            model.forward_inference(host1)['pred_wp'].cpu()
-        lat_host = (time.perf_counter() - t0) * 1e3 / 20
+        lat_host = None
+        try:                                                     # an extra key: never at the price of the bench line
+            for k in ('img', 'points', 'speed', 'target_point', 'target_command'):
+                host1[k] = host1[k].pin_memory()
+            for _ in range(4):
+                model.forward_inference(host1)['pred_wp'].cpu()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                model.forward_inference(host1)['pred_wp'].cpu()
+            lat_host = (time.perf_counter() - t0) * 1e3 / 20
+        except Exception as ex:                                  # noqa: BLE001
+            print(f'[bench] closed-loop host-input latency skipped: {ex!r}', file=sys.stderr)
 
     if rank != 0:
         if world > 1:
@@ -403,7 +407,7 @@ def main():
     if lat is not None:
         line['latency_b1'] = {'ms_per_frame': lat, 'frames_per_s': 1000.0 / lat,
                               'note': 'configs[1]: one frame per forward (closed-loop mode), same model, CUDA-graph replay, inputs resident',
-                              'e2e_host_inputs': {'ms_per_frame': lat_host, 'frames_per_s': 1000.0 / lat_host,
+                              'e2e_host_inputs': None if lat_host is None else {'ms_per_frame': lat_host, 'frames_per_s': 1000.0 / lat_host,
                                                   'note': 'wall clock per call with the batch in pinned host memory (38.5 MB of images uploaded inside the call, '
                                                           'pipelined against the kernels) and the waypoints read back: what the closed-loop agent pays per tick'},
                               'streaming_bev_cache': {'ms_per_frame': lat_stream, 'frames_per_s': 1000.0 / lat_stream,
