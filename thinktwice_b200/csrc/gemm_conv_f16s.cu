@@ -1059,8 +1059,9 @@ cudaError_t launch_f16s(cudaLaunchConfig_t& cfg, const CUtensorMap& ma, const CU
   if constexpr (GATHER == 0) {
     if (pair && a.d.KH * a.d.KW == 1 && !(g_tt_debug & 0x400000) && !a.res2 && !a.res2_s) return launch_f16s_v<BN, STAGES, GATHER, true, 16>(cfg, ma, mb, a);
   }
-  // cta_group::2 (one MMA of the pair's leader over M = 256, each SM reading only half of the weight rows): the long-K dense layers,
-  // whose pace is set by the shared-memory operand reads.  EXPERIMENT behind debug bit 0x2000000 until measured.
+  // cta_group::2 (one MMA of the pair's leader over M = 256, each SM reading only half of the weight rows).  Measured (profiles/r2_summary.md):
+  // parity green, no gain on the long-K layers (341 -> 336 us; 8 x images: slower) — their pace is set by the barrier ring and the epilogue's
+  // store phase, not by the operand reads.  Kept behind debug bit 0x2000000 as the starting point of a deeper-pipelined pair kernel.
   if constexpr (GATHER == 0 && BN == 128) {
     if (pair && (g_tt_debug & 0x2000000) && !a.corr_once) return launch_f16s_co<BN, STAGES, GATHER, true, 8, false, 2>(cfg, ma, mb, a);
   }
