@@ -44,7 +44,8 @@ def emulated(monkeypatch):
     import thinktwice_b200.lidarnet as lidarnet
     import thinktwice_b200.thinktwice_decoder as dec
     import thinktwice_b200.encoder_decoder_framework as fw
-    for mod in (engine, lss, lidarnet, dec, fw):
+    import thinktwice_b200.preprocess as pre
+    for mod in (engine, lss, lidarnet, dec, fw, pre):
         monkeypatch.setattr(mod, '_p', p, raising=False)
         monkeypatch.setattr(mod, '_stream', lib._stream, raising=False)
     return emu

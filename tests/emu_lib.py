@@ -221,6 +221,32 @@ class Emu:
             dst[:, top:top + H, left:left + W, Cc:] = 0
         return 0
 
+    def tt_preprocess_u8(self, d, raw, map_grid, out_nchw, out_split8, split_plane, stream):
+        """include/tt_b200.h section 8: uint8 HWC frames -> grid_sample -> bilinear resize -> crop -> / div -> (x - mean) / std, written as
+        fp32 NCHW and / or the stem's split planes (plain torch ops: the semantics, not the kernel's operation order)."""
+        self.launches += 1
+        d = _desc(d)
+        n, H, W = d.n_img, d.H, d.W
+        x = raw.flat()[:n * H * W * 3].view(n, H, W, 3).float().permute(0, 3, 1, 2)
+        if d.undistort:
+            g = map_grid.flat()[:H * W * 2].view(1, H, W, 2).expand(n, H, W, 2)
+            x = F.grid_sample(x, g, mode='bilinear', padding_mode='zeros', align_corners=False)
+        x = F.interpolate(x, size=(d.newH, d.newW), mode='bilinear', align_corners=False, antialias=False)
+        x = x[:, :, d.crop_y:d.crop_y + d.outH, d.crop_x:d.crop_x + d.outW]
+        mean = torch.tensor(list(d.mean)).view(1, 3, 1, 1)
+        std = torch.tensor(list(d.std)).view(1, 3, 1, 1)
+        x = (x / d.div - mean) / std
+        if out_nchw:
+            out_nchw.flat()[:x.numel()].copy_(x.reshape(-1))
+        if out_split8:
+            plane = _v(split_plane)
+            hi, lo = _split_f16(x.permute(0, 2, 3, 1))
+            for off, val in ((0, hi), (plane, lo)):
+                dst = Ptr(out_split8.t, out_split8.off + off).flat()[:n * d.pad_H * d.pad_W * 8].view(n, d.pad_H, d.pad_W, 8)
+                dst[:, d.pad_top:d.pad_top + d.outH, d.pad_left:d.pad_left + d.outW, :3] = val
+                dst[:, d.pad_top:d.pad_top + d.outH, d.pad_left:d.pad_left + d.outW, 3:] = 0
+        return 0
+
     def tt_upsample2x_bilinear_ac_split(self, x, y_split, y_plane, N, H, W, Cc, stream):
         self.launches += 1
         y_plane = _v(y_plane)

@@ -77,3 +77,29 @@ def test_full_thinktwice_config_through_the_emulated_abi_matches_the_oracle(emul
     cam = m.last_cam_feat
     assert rel(cam['seg'].nchw(), keep['cam']['seg']) < 5e-4
     assert rel(cam['bev'].nchw(), keep['cam']['bev']) < 5e-4
+
+
+@pytest.mark.parametrize('impl', [4, 1])
+def test_raw_uint8_frames_through_the_emulated_abi_match_the_preprocessed_tensor(emulated, impl):
+    """SURVEY 8f f1 host plumbing on the CPU: a batch carrying `img_raw` (uint8 frames; per-sweep uint8 staging buffers, the pre-processor
+    writing the stem's operand planes — impl 4 — or the NCHW tensor the fp32 engines stage themselves — impl 1) against the same model fed
+    with the oracle's pre-processed `img`."""
+    from oracle import preprocess as op
+    from thinktwice_b200.config import PLUMBING_CONFIG
+    from thinktwice_b200.preprocess import AgentPreprocessor
+    o, m, batch = _pair(PLUMBING_CONFIG, 1, 1200, 7, impl, sweeps=2)
+    conf = {'final_dim': (256, 256), 'H': 300, 'W': 400, 'bot_pct_lim': (0.0, 0.0)}
+    ys, xs = torch.meshgrid(torch.arange(300.), torch.arange(400.), indexing='ij')
+    grid = torch.stack([(xs + 2 * torch.sin(ys / 31) - 200) / 200, (ys + 1.5 * torch.cos(xs / 47) - 150) / 150], -1)
+    raw = torch.from_numpy(np.random.default_rng(5).integers(0, 256, size=(1, 2, 4, 300, 400, 3), dtype=np.uint8))
+    batch['img'] = op.image_normalize(op.ida_image_transform(raw[0], grid, conf)[0])[None]
+    want = {k: m.forward_inference(batch)[k].clone() for k in ('pred_wp', 'mu_branches', 'refine_BEV_feature')}
+    m.attach_preprocessor(AgentPreprocessor(dict(undistort=True, num_cams=4), conf, 'cpu', map_grid=grid))
+    rb = {k: v for k, v in batch.items() if k != 'img'}
+    rb['img_raw'] = raw
+    got = m.forward_inference(rb)
+    for k, v in want.items():
+        assert rel(got[k], v) < 1e-5, k
+    with pytest.raises(Exception):                                      # without a pre-processor the raw batch is refused, not guessed at
+        m.img_encoder.pre = None
+        m.forward_inference(rb)
