@@ -416,10 +416,15 @@ class EncoderDecoder(nn.Module):
             fresh_key = use_graph and ('pipe',) + key not in self._graphs
             if fresh_key:
                 self._graphs[('pipe',) + key] = None               # (eager pass: _pipelined_forward sees no graphs yet)
-            pred = self._own(self._pipelined_forward(img, key, batch))
-            if fresh_key:
-                torch.cuda.synchronize()
-                self._capture_pipeline(key)
+            try:
+                pred = self._own(self._pipelined_forward(img, key, batch))
+                if fresh_key:
+                    torch.cuda.synchronize()
+                    self._capture_pipeline(key)
+            except BaseException:
+                if fresh_key:
+                    self._graphs.pop(('pipe',) + key, None)        # a failed first call must not leave the key marked as 'eager for ever'
+                raise
         else:
             for t in range(0 if not warm else T - 1, T):
                 self._stage_sweep(img, t)
