@@ -110,3 +110,20 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, f'{cname}.{fname}'
+
+
+def test_new_entry_points_fail_loudly_without_cuda_too():
+    """rows f1 / f4: the GPU pre-processor and the MSDA function refuse CPU devices / tensors instead of falling back."""
+    import pytest
+    import torch
+    from thinktwice_b200 import lib
+    from thinktwice_b200.ops.ms_deform_attn import MultiScaleDeformableAttnFunction_fp32
+    from thinktwice_b200.preprocess import AgentPreprocessor
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    with pytest.raises(lib.TTError):
+        AgentPreprocessor(dict(undistort=False, num_cams=1), {'final_dim': (4, 4), 'H': 8, 'W': 8, 'bot_pct_lim': (0.0, 0.0)}, 'cpu')
+    v = torch.zeros(1, 4, 2, 8)
+    loc, aw = torch.zeros(1, 3, 2, 1, 4, 2), torch.zeros(1, 3, 2, 1, 4)
+    with pytest.raises(lib.TTError):
+        MultiScaleDeformableAttnFunction_fp32.apply(v, torch.tensor([[2, 2]]), torch.tensor([0]), loc, aw, 64)
